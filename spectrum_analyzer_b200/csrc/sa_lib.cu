@@ -1,0 +1,523 @@
+// sa_lib.cu -- C ABI of libspectrum_analyzer_cuda.so (see include/spectrum_analyzer_cuda.h).
+//
+// Host side: context (device, stream, cached twiddle/window tables, staging buffers), argument
+// validation with the reference's error taxonomy and precedence (src/lib.rs:164-181, 317), kernel
+// dispatch per N, and the host-buffer pipeline (pinned staging, H2D / compute / D2H on three
+// streams).  There is no CPU compute path: every spectrum is produced by the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sa_aux_kernels.cuh"
+#include "sa_host_math.h"
+#include "sa_spectrum_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int cuda_fail(cudaError_t e, const char *what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return SA_ERR_CUDA;
+}
+#define SA_CUDA(call)                                          \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+  } while (0)
+
+int log2_exact(uint64_t n) {
+  int l = 0;
+  while ((1ull << l) < n) l++;
+  return l;
+}
+
+struct KernelPlan {
+  int max_blocks = 0;   // resident CTAs on the whole device
+  bool ready = false;
+};
+
+}  // namespace
+
+struct sa_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  uint64_t launches = 0;
+  std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
+  std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
+  KernelPlan plans[16];                                     // per log2n
+  // host-buffer pipeline
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  static constexpr int kSlots = 3;
+  float *slot_in[kSlots] = {nullptr, nullptr, nullptr};
+  float *slot_out[kSlots] = {nullptr, nullptr, nullptr};
+  sa_frame_stats *slot_stats[kSlots] = {nullptr, nullptr, nullptr};
+  size_t slot_in_bytes = 0, slot_out_bytes = 0, slot_stats_bytes = 0;
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
+  bool pipeline_ready = false;
+};
+
+namespace {
+
+using namespace sa;
+
+int get_twiddle(sa_ctx *ctx, uint32_t n, const float2 **out) {
+  auto it = ctx->twiddles.find(n);
+  if (it == ctx->twiddles.end()) {
+    std::vector<float> host = sa_host::twiddle_table(n);
+    float2 *dev = nullptr;
+    SA_CUDA(cudaMalloc(&dev, host.size() * sizeof(float)));
+    SA_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));  // `host` goes out of scope
+    it = ctx->twiddles.emplace(n, dev).first;
+  }
+  *out = it->second;
+  return SA_OK;
+}
+
+int get_window(sa_ctx *ctx, int kind, uint32_t n, const float **out) {
+  if (kind == SA_WINDOW_NONE) { *out = nullptr; return SA_OK; }
+  auto key = std::make_pair(kind, n);
+  auto it = ctx->windows.find(key);
+  if (it == ctx->windows.end()) {
+    std::vector<float> host(n);
+    for (uint32_t i = 0; i < n; i++) host[i] = sa_host::window_multiplier(kind, i, n);
+    float *dev = nullptr;
+    SA_CUDA(cudaMalloc(&dev, n * sizeof(float)));
+    SA_CUDA(cudaMemcpyAsync(dev, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->windows.emplace(key, dev).first;
+  }
+  *out = it->second;
+  return SA_OK;
+}
+
+template <class C>
+int launch_cfg(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
+  KernelPlan &plan = ctx->plans[log2n];
+  auto kernel = spectrum_kernel<C>;
+  if (!plan.ready) {
+    SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TOTAL));
+    int per_sm = 0;
+    SA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::NT, C::SMEM_TOTAL));
+    if (per_sm < 1) { g_last_error = "kernel does not fit on an SM"; return SA_ERR_CUDA; }
+    plan.max_blocks = per_sm * ctx->num_sms;
+    plan.ready = true;
+  }
+  const u64 needed = (p.n_frames + C::FPB - 1) / C::FPB;
+  const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
+  kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(p);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
+  if (p.n_frames == 0) return SA_OK;
+  switch (log2n) {
+    case 1: case 2: case 3: case 4: case 5: {
+      const unsigned grid = (unsigned)((p.n_frames + 127) / 128);
+      spectrum_tiny_kernel<<<grid, 128, 0, ctx->stream>>>(p, log2n);
+      ctx->launches++;
+      SA_CUDA(cudaGetLastError());
+      return SA_OK;
+    }
+    case 6: return launch_cfg<SpectrumCfg<6, 8, 32>>(ctx, p, log2n);
+    case 7: return launch_cfg<SpectrumCfg<7, 8, 16>>(ctx, p, log2n);
+    case 8: return launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n);
+    case 9: return launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n);
+    case 10: return launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n);
+    case 11: return launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n);
+    case 12: return launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n);
+    case 13: return launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n);
+    case 14: return launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n);
+    case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
+    default: return SA_ERR_UNSUPPORTED_LENGTH;
+  }
+}
+
+// Call-level validation in the reference's order (src/lib.rs:164-181, src/fft.rs:52, src/lib.rs:317).
+int validate_call(uint64_t n, uint32_t sampling_rate, int limit_kind, float lo, float hi, int window_kind,
+                  int scaling_kind, uint32_t *bin_lo, uint32_t *n_bins) {
+  if (window_kind < SA_WINDOW_NONE || window_kind > SA_WINDOW_BLACKMAN_HARRIS_7TERM) return SA_ERR_INVALID_ARGUMENT;
+  if (scaling_kind < SA_SCALING_NONE || scaling_kind > SA_SCALING_20_TIMES_LOG10) return SA_ERR_INVALID_ARGUMENT;
+  if (limit_kind < SA_LIMIT_ALL || limit_kind > SA_LIMIT_RANGE) return SA_ERR_INVALID_ARGUMENT;
+  if (n < 2) return SA_ERR_TOO_FEW_SAMPLES;
+  if (n & (n - 1)) return SA_ERR_NOT_POWER_OF_TWO;
+  const int e = sa_host::limit_verify(limit_kind, lo, hi, (float)sampling_rate / 2.0f);
+  if (e != SA_OK) return e;
+  if (n > 32768) return SA_ERR_UNSUPPORTED_LENGTH;
+  sa_host::limit_bins((uint32_t)n, sampling_rate, limit_kind, lo, hi, bin_lo, n_bins);
+  if (*n_bins < 2) return SA_ERR_LIMIT_TOO_NARROW;
+  return SA_OK;
+}
+
+int fill_params(sa_ctx *ctx, SpectrumParams &p, const float *d_samples, uint64_t n_frames, uint32_t n,
+                uint64_t frame_stride, int window_kind, int scaling_kind, uint32_t stats_mask, float *d_out,
+                uint64_t out_stride, sa_frame_stats *d_stats, uint32_t bin_lo, uint32_t n_bins) {
+  int e;
+  if ((e = get_twiddle(ctx, n, &p.twiddle)) != SA_OK) return e;
+  if ((e = get_window(ctx, window_kind, n, &p.window)) != SA_OK) return e;
+  p.samples = d_samples;
+  p.out_vals = d_out;
+  p.stats = (stats_mask & SA_STATS_ALL) ? d_stats : nullptr;
+  p.n_frames = n_frames;
+  p.frame_stride = frame_stride;
+  p.out_stride = out_stride;
+  p.bin_lo = bin_lo;
+  p.bin_hi = bin_lo + n_bins - 1;
+  p.scaling_kind = scaling_kind;
+  p.stats_mask = stats_mask & SA_STATS_ALL;
+  const float nf = (float)n;  // stats.n = samples_len as f32 (src/spectrum.rs:144)
+  p.scale_div = scaling_kind == SA_SCALING_DIVIDE_BY_N_SQRT ? sqrtf(nf) : nf;
+  p.aligned8 = ((reinterpret_cast<uintptr_t>(d_samples) & 7u) == 0 && (frame_stride & 1u) == 0) ? 1 : 0;
+  return SA_OK;
+}
+
+int ensure_pipeline(sa_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t stats_bytes) {
+  if (!ctx->pipeline_ready) {
+    SA_CUDA(cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+    SA_CUDA(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+    for (int s = 0; s < sa_ctx::kSlots; s++) {
+      SA_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
+      SA_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[s], cudaEventDisableTiming));
+      SA_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[s], cudaEventDisableTiming));
+    }
+    ctx->pipeline_ready = true;
+  }
+  for (int s = 0; s < sa_ctx::kSlots; s++) {
+    if (ctx->slot_in_bytes < in_bytes) {
+      if (ctx->slot_in[s]) SA_CUDA(cudaFree(ctx->slot_in[s]));
+      ctx->slot_in[s] = nullptr;
+      SA_CUDA(cudaMalloc(&ctx->slot_in[s], in_bytes));
+    }
+    if (ctx->slot_out_bytes < out_bytes) {
+      if (ctx->slot_out[s]) SA_CUDA(cudaFree(ctx->slot_out[s]));
+      ctx->slot_out[s] = nullptr;
+      SA_CUDA(cudaMalloc(&ctx->slot_out[s], out_bytes));
+    }
+    if (ctx->slot_stats_bytes < stats_bytes) {
+      if (ctx->slot_stats[s]) SA_CUDA(cudaFree(ctx->slot_stats[s]));
+      ctx->slot_stats[s] = nullptr;
+      SA_CUDA(cudaMalloc(&ctx->slot_stats[s], stats_bytes));
+    }
+  }
+  ctx->slot_in_bytes = std::max(ctx->slot_in_bytes, in_bytes);
+  ctx->slot_out_bytes = std::max(ctx->slot_out_bytes, out_bytes);
+  ctx->slot_stats_bytes = std::max(ctx->slot_stats_bytes, stats_bytes);
+  return SA_OK;
+}
+
+// Page-locks a caller buffer for the duration of a call unless it already is CUDA host memory.
+struct ScopedPin {
+  void *ptr = nullptr;
+  bool registered = false;
+  void pin(const void *p, size_t bytes) {
+    if (!p || bytes < (1u << 20)) return;  // small copies: pageable is fine
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type != cudaMemoryTypeUnregistered) return;
+    (void)cudaGetLastError();
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+      ptr = const_cast<void *>(p);
+      registered = true;
+    } else {
+      (void)cudaGetLastError();  // fall back to pageable copies (slower, still correct)
+    }
+  }
+  ~ScopedPin() { if (registered) cudaHostUnregister(ptr); }
+};
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+uint32_t sa_abi_version(void) { return SA_ABI_VERSION; }
+
+const char *sa_status_string(int status) {
+  switch (status) {
+    case SA_OK: return "ok";
+    case SA_ERR_TOO_FEW_SAMPLES: return "Too few samples!";
+    case SA_ERR_NAN_VALUES: return "NaN values are not supported!";
+    case SA_ERR_INFINITY_VALUES: return "Infinity values are not supported!";
+    case SA_ERR_NOT_POWER_OF_TWO: return "Samples length must be a power of two!";
+    case SA_ERR_LIMIT_BELOW_MINIMUM: return "Invalid frequency limit: Value below minimum";
+    case SA_ERR_LIMIT_ABOVE_NYQUIST: return "Invalid frequency limit: Value above Nyquist";
+    case SA_ERR_LIMIT_INVALID_RANGE: return "Invalid frequency limit: Invalid range";
+    case SA_ERR_LIMIT_TOO_NARROW: return "Frequency limit leaves too few frequency bins!";
+    case SA_ERR_SCALING: return "Scaling error";
+    case SA_ERR_UNSUPPORTED_LENGTH: return "should be one of the supported buffer lengths (2..32768)";
+    case SA_ERR_NON_FINITE_RESULT: return "NaN/Infinite-values are not supported! (non-finite spectrum value)";
+    case SA_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case SA_ERR_CUDA: return "CUDA error (see sa_last_error_string)";
+    case SA_ERR_OUT_OF_MEMORY: return "out of memory";
+    default: return "unknown status";
+  }
+}
+
+const char *sa_last_error_string(void) { return g_last_error.c_str(); }
+
+int sa_ctx_create_on_stream(int device, void *cuda_stream, sa_ctx **out_ctx) {
+  if (!out_ctx) return SA_ERR_INVALID_ARGUMENT;
+  *out_ctx = nullptr;
+  int count = 0;
+  SA_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) { g_last_error = "no such CUDA device"; return SA_ERR_CUDA; }
+  SA_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SA_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    g_last_error = std::string("device is not sm_100 class: ") + prop.name;
+    return SA_ERR_CUDA;
+  }
+  sa_ctx *ctx = new sa_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  *out_ctx = ctx;
+  return SA_OK;
+}
+
+int sa_ctx_create(int device, sa_ctx **out_ctx) {
+  int e = sa_ctx_create_on_stream(device, nullptr, out_ctx);
+  if (e != SA_OK) return e;
+  cudaStream_t s;
+  cudaError_t ce = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { delete *out_ctx; *out_ctx = nullptr; return cuda_fail(ce, "cudaStreamCreateWithFlags"); }
+  (*out_ctx)->stream = s;
+  (*out_ctx)->owns_stream = true;
+  return SA_OK;
+}
+
+int sa_ctx_destroy(sa_ctx *ctx) {
+  if (!ctx) return SA_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->twiddles) cudaFree(kv.second);
+  for (auto &kv : ctx->windows) cudaFree(kv.second);
+  for (int s = 0; s < sa_ctx::kSlots; s++) {
+    cudaFree(ctx->slot_in[s]); cudaFree(ctx->slot_out[s]); cudaFree(ctx->slot_stats[s]);
+    if (ctx->pipeline_ready) { cudaEventDestroy(ctx->ev_h2d[s]); cudaEventDestroy(ctx->ev_comp[s]); cudaEventDestroy(ctx->ev_d2h[s]); }
+  }
+  if (ctx->pipeline_ready) { cudaStreamDestroy(ctx->h2d); cudaStreamDestroy(ctx->d2h); }
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SA_OK;
+}
+
+int sa_ctx_sync(sa_ctx *ctx) {
+  if (!ctx) return SA_ERR_INVALID_ARGUMENT;
+  SA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SA_OK;
+}
+
+uint64_t sa_ctx_launch_count(const sa_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int sa_window_coeffs(int window_kind, uint32_t n, float *host_out) {
+  if (!host_out || window_kind < SA_WINDOW_NONE || window_kind > SA_WINDOW_BLACKMAN_HARRIS_7TERM || n > 32768)
+    return SA_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < n; i++) host_out[i] = sa_host::window_multiplier(window_kind, i, n);
+  return SA_OK;
+}
+
+int sa_limit_to_bins(uint32_t n, uint32_t sampling_rate, int limit_kind, float limit_lo, float limit_hi,
+                     uint32_t *bin_lo, uint32_t *n_bins) {
+  uint32_t lo = 0, nb = 0;
+  const int e = validate_call(n, sampling_rate, limit_kind, limit_lo, limit_hi, SA_WINDOW_NONE, SA_SCALING_NONE, &lo, &nb);
+  if (bin_lo) *bin_lo = lo;
+  if (n_bins) *n_bins = nb;
+  return e;
+}
+
+int sa_bin_frequencies(uint32_t n, uint32_t sampling_rate, uint32_t bin_lo, uint32_t n_bins, float *host_out) {
+  if (!host_out || n == 0) return SA_ERR_INVALID_ARGUMENT;
+  const volatile float res = (float)sampling_rate / (float)n;  // src/lib.rs:356-358
+  for (uint32_t i = 0; i < n_bins; i++) {
+    volatile float f = (float)(bin_lo + i) * res;              // src/lib.rs:278
+    host_out[i] = f;
+  }
+  return SA_OK;
+}
+
+int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, uint32_t n, uint64_t frame_stride,
+                        uint32_t sampling_rate, int limit_kind, float limit_lo, float limit_hi, int window_kind,
+                        int scaling_kind, uint32_t stats_mask, float *d_out_vals, uint64_t out_stride,
+                        sa_frame_stats *d_stats, uint32_t *bin_lo, uint32_t *n_bins) {
+  if (!ctx) return SA_ERR_INVALID_ARGUMENT;
+  uint32_t lo = 0, nb = 0;
+  const int e = validate_call(n, sampling_rate, limit_kind, limit_lo, limit_hi, window_kind, scaling_kind, &lo, &nb);
+  if (bin_lo) *bin_lo = lo;
+  if (n_bins) *n_bins = nb;
+  if (e != SA_OK) return e;
+  if (n_frames == 0) return SA_OK;
+  if (!d_samples || !d_out_vals || out_stride < nb || frame_stride == 0) return SA_ERR_INVALID_ARGUMENT;
+  if ((stats_mask & SA_STATS_ALL) && !d_stats) return SA_ERR_INVALID_ARGUMENT;
+  SA_CUDA(cudaSetDevice(ctx->device));
+  SpectrumParams p;
+  int pe = fill_params(ctx, p, d_samples, n_frames, n, frame_stride, window_kind, scaling_kind, stats_mask,
+                       d_out_vals, out_stride, d_stats, lo, nb);
+  if (pe != SA_OK) return pe;
+  return launch_spectrum(ctx, p, log2_exact(n));
+}
+
+int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_frames, uint32_t n,
+                             uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                             float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
+                             float *h_out_vals, uint64_t out_stride, sa_frame_stats *h_stats, uint32_t *bin_lo,
+                             uint32_t *n_bins) {
+  if (!ctx) return SA_ERR_INVALID_ARGUMENT;
+  uint32_t lo = 0, nb = 0;
+  const int e = validate_call(n, sampling_rate, limit_kind, limit_lo, limit_hi, window_kind, scaling_kind, &lo, &nb);
+  if (bin_lo) *bin_lo = lo;
+  if (n_bins) *n_bins = nb;
+  if (e != SA_OK) return e;
+  if (n_frames == 0) return SA_OK;
+  if (!h_samples || !h_out_vals || out_stride < nb || frame_stride == 0) return SA_ERR_INVALID_ARGUMENT;
+  const bool want_stats = (stats_mask & SA_STATS_ALL) != 0;
+  if (want_stats && !h_stats) return SA_ERR_INVALID_ARGUMENT;
+  SA_CUDA(cudaSetDevice(ctx->device));
+
+  // chunking: ~64 MiB of unique input per chunk
+  const uint64_t target = 64ull << 20;
+  uint64_t chunk = std::max<uint64_t>(1, target / (frame_stride * sizeof(float)));
+  chunk = std::min(chunk, n_frames);
+  const size_t in_bytes = ((chunk - 1) * frame_stride + n) * sizeof(float);
+  const size_t out_bytes = chunk * out_stride * sizeof(float);
+  const size_t st_bytes = chunk * sizeof(sa_frame_stats);
+  int pe = ensure_pipeline(ctx, in_bytes, out_bytes, st_bytes);
+  if (pe != SA_OK) return pe;
+
+  ScopedPin pin_in, pin_out, pin_st;
+  pin_in.pin(h_samples, ((n_frames - 1) * frame_stride + n) * sizeof(float));
+  pin_out.pin(h_out_vals, ((n_frames - 1) * out_stride + nb) * sizeof(float));
+  if (want_stats) pin_st.pin(h_stats, n_frames * sizeof(sa_frame_stats));
+
+  const int log2n = log2_exact(n);
+  uint64_t c = 0;
+  for (uint64_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
+    const int s = (int)(c % sa_ctx::kSlots);
+    const uint64_t nf = std::min(chunk, n_frames - f0);
+    if (c >= (uint64_t)sa_ctx::kSlots) {
+      SA_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[s], 0));     // input slot consumed
+      SA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));   // output slot drained
+    }
+    SA_CUDA(cudaMemcpyAsync(ctx->slot_in[s], h_samples + f0 * frame_stride,
+                            ((nf - 1) * frame_stride + n) * sizeof(float), cudaMemcpyHostToDevice, ctx->h2d));
+    SA_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->h2d));
+    SA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
+    SpectrumParams p;
+    pe = fill_params(ctx, p, ctx->slot_in[s], nf, n, frame_stride, window_kind, scaling_kind, stats_mask,
+                     ctx->slot_out[s], out_stride, ctx->slot_stats[s], lo, nb);
+    if (pe != SA_OK) return pe;
+    pe = launch_spectrum(ctx, p, log2n);
+    if (pe != SA_OK) return pe;
+    SA_CUDA(cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+    SA_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[s], 0));
+    SA_CUDA(cudaMemcpyAsync(h_out_vals + f0 * out_stride, ctx->slot_out[s],
+                            ((nf - 1) * out_stride + nb) * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
+    if (want_stats)
+      SA_CUDA(cudaMemcpyAsync(h_stats + f0, ctx->slot_stats[s], nf * sizeof(sa_frame_stats),
+                              cudaMemcpyDeviceToHost, ctx->d2h));
+    SA_CUDA(cudaEventRecord(ctx->ev_d2h[s], ctx->d2h));
+  }
+  SA_CUDA(cudaStreamSynchronize(ctx->d2h));
+  SA_CUDA(cudaStreamSynchronize(ctx->stream));
+  SA_CUDA(cudaStreamSynchronize(ctx->h2d));
+  return SA_OK;
+}
+
+int sa_spectrum_single(sa_ctx *ctx, const float *h_samples, uint64_t n_samples, uint32_t sampling_rate,
+                       int limit_kind, float limit_lo, float limit_hi, int window_kind, int scaling_kind,
+                       float *h_freqs, float *h_vals, uint32_t *n_bins, sa_frame_stats *h_stats) {
+  if (!ctx) return SA_ERR_INVALID_ARGUMENT;
+  if (n_bins) *n_bins = 0;
+  if (window_kind < SA_WINDOW_NONE || window_kind > SA_WINDOW_BLACKMAN_HARRIS_7TERM) return SA_ERR_INVALID_ARGUMENT;
+  // src/lib.rs:164-176: length, then NaN, then Inf (of the samples handed to the FFT, i.e. after
+  // the window), then power of two.  This scan is argument validation only.
+  if (n_samples < 2) return SA_ERR_TOO_FEW_SAMPLES;
+  if (!h_samples) return SA_ERR_INVALID_ARGUMENT;
+  {
+    bool any_nan = false, any_inf = false;
+    for (uint64_t i = 0; i < n_samples; i++) {
+      float v = h_samples[i];
+      if (window_kind != SA_WINDOW_NONE) v = sa_host::window_multiplier(window_kind, (uint32_t)i, (uint32_t)n_samples) * v;
+      any_nan |= std::isnan(v);
+      any_inf |= std::isinf(v);
+    }
+    if (any_nan) return SA_ERR_NAN_VALUES;
+    if (any_inf) return SA_ERR_INFINITY_VALUES;
+  }
+  uint32_t lo = 0, nb = 0;
+  const int e = validate_call(n_samples, sampling_rate, limit_kind, limit_lo, limit_hi, window_kind, scaling_kind, &lo, &nb);
+  if (e != SA_OK) return e;
+  if (!h_vals) return SA_ERR_INVALID_ARGUMENT;
+  sa_frame_stats st;
+  std::memset(&st, 0, sizeof st);
+  const uint32_t n = (uint32_t)n_samples;
+  const int r = sa_spectrum_batched_host(ctx, h_samples, 1, n, n, sampling_rate, limit_kind, limit_lo, limit_hi,
+                                         window_kind, scaling_kind, SA_STATS_ALL, h_vals, nb, &st, nullptr, nullptr);
+  if (r != SA_OK) return r;
+  if (st.status != SA_OK) return (int)st.status;
+  if (h_freqs) sa_bin_frequencies(n, sampling_rate, lo, nb, h_freqs);
+  if (n_bins) *n_bins = nb;
+  if (h_stats) *h_stats = st;
+  return SA_OK;
+}
+
+int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint32_t n_bins, uint64_t stride,
+                             uint32_t bin_lo, uint32_t n, int scaling_kind, uint32_t stats_mask,
+                             sa_frame_stats *d_stats) {
+  if (!ctx || !d_vals || !d_stats || n_bins < 2 || stride < n_bins || n < 2) return SA_ERR_INVALID_ARGUMENT;
+  if (scaling_kind < SA_SCALING_NONE || scaling_kind > SA_SCALING_20_TIMES_LOG10) return SA_ERR_INVALID_ARGUMENT;
+  if (n_frames == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(ctx->device));
+  const float nf = (float)n;
+  const float div = scaling_kind == SA_SCALING_DIVIDE_BY_N_SQRT ? sqrtf(nf) : nf;
+  const unsigned grid = (unsigned)std::min<uint64_t>(n_frames, (uint64_t)ctx->num_sms * 8);
+  sa::rescale_kernel<<<grid, sa::RESCALE_THREADS, 0, ctx->stream>>>(d_vals, n_frames, n_bins, stride, bin_lo, scaling_kind,
+                                                                    div, stats_mask & SA_STATS_ALL, d_stats);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t n_frames, uint32_t n,
+                      uint64_t frame_stride, float *d_out) {
+  if (!ctx || !d_in || !d_out || n == 0 || n > 32768) return SA_ERR_INVALID_ARGUMENT;
+  if (window_kind < SA_WINDOW_NONE || window_kind > SA_WINDOW_BLACKMAN_HARRIS_7TERM) return SA_ERR_INVALID_ARGUMENT;
+  if (n_frames == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(ctx->device));
+  const float *w = nullptr;
+  int e = get_window(ctx, window_kind, n, &w);
+  if (e != SA_OK) return e;
+  const uint64_t total = n_frames * n;
+  const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 16);
+  sa::window_kernel<<<grid, 256, 0, ctx->stream>>>(d_in, w, d_out, n_frames, n, frame_stride);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+int sa_generate_noise(sa_ctx *ctx, float *d_out, uint64_t first_index, uint64_t count, uint64_t seed) {
+  if (!ctx || (!d_out && count)) return SA_ERR_INVALID_ARGUMENT;
+  if (count == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx->num_sms * 16);
+  sa::noise_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, first_index, count, seed);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+}  // extern "C"
