@@ -109,22 +109,25 @@ def test_scalings(gpu_ctx, n, scaling):
     check_against_oracle(x, frames, n, n, 44100, (O.LIMIT_ALL, 0, 0), O.WINDOW_HANN, scaling)
 
 
-@pytest.mark.parametrize("n,limit", [
-    (2048, (O.LIMIT_MAX, 0.0, 4000.0)),          # cfg1 (the repo's own test case)
-    (4096, (O.LIMIT_MAX, 0.0, 4000.0)),
-    (16384, (O.LIMIT_RANGE, 50.0, 15000.0)),     # cfg4
-    (512, (O.LIMIT_MIN, 100.0, 0.0)),
-    (512, (O.LIMIT_RANGE, 412.0, 510.0)),
-    (256, (O.LIMIT_RANGE, 1000.0, 1400.0)),      # 3 bins (odd count)
-    (256, (O.LIMIT_RANGE, 1000.0, 1250.0)),      # 2 bins (even count, smallest legal)
-    (64, (O.LIMIT_MAX, 0.0, 700.0)),
-    (8, (O.LIMIT_MIN, 11000.0, 0.0)),
+@pytest.mark.parametrize("n,sr,limit", [
+    (2048, 44100, (O.LIMIT_MAX, 0.0, 4000.0)),          # cfg1 (the repo's own test case)
+    (4096, 44100, (O.LIMIT_MAX, 0.0, 4000.0)),
+    (16384, 44100, (O.LIMIT_RANGE, 50.0, 15000.0)),     # cfg4
+    (512, 1024, (O.LIMIT_MIN, 100.0, 0.0)),             # src/tests/mod.rs:224-290
+    (512, 1024, (O.LIMIT_MAX, 0.0, 400.0)),
+    (512, 1024, (O.LIMIT_RANGE, 412.0, 510.0)),
+    (256, 44100, (O.LIMIT_RANGE, 1000.0, 1400.0)),      # 3 bins (odd count)
+    (256, 44100, (O.LIMIT_RANGE, 1000.0, 1250.0)),      # 2 bins (even count, smallest legal)
+    (64, 44100, (O.LIMIT_MAX, 0.0, 700.0)),
+    (8, 44100, (O.LIMIT_MIN, 11000.0, 0.0)),
+    (32768, 96000, (O.LIMIT_RANGE, 20.0, 20000.0)),
 ])
-def test_frequency_limits(gpu_ctx, n, limit):
-    frames = 11
+def test_frequency_limits(gpu_ctx, n, sr, limit):
+    frames = 11 if n <= 4096 else 3
     x = noise(frames, n, seed=7 * n)
+    assert O.limit_to_bins(n, sr, *limit)[1] >= 2
     for sc in (O.SCALING_NONE, O.SCALING_ZERO_TO_ONE, O.SCALING_20_TIMES_LOG10):
-        check_against_oracle(x, frames, n, n, 44100, limit, O.WINDOW_BH4, sc)
+        check_against_oracle(x, frames, n, n, sr, limit, O.WINDOW_BH4, sc)
 
 
 def test_host_pipeline_matches_device_path(gpu_ctx):
