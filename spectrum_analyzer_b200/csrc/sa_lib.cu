@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -18,6 +19,7 @@
 #include "sa_aux_kernels.cuh"
 #include "sa_host_math.h"
 #include "sa_spectrum_kernel.cuh"
+#include "sa_spectrum_v2.cuh"
 
 namespace {
 
@@ -52,9 +54,12 @@ struct sa_ctx {
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   uint64_t launches = 0;
+  bool use_generic = false;   // SA_FORCE_GENERIC=1: run the generic kernel family for every N (A/B testing)
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
-  KernelPlan plans[16];                                     // per log2n
+  KernelPlan plans[16];                                     // per log2n (generic family)
+  KernelPlan plans_v2[16][4][2];                            // tuned family: [log2n][scale mode][full range]
+  std::map<uint32_t, float2 *> v2_tables;                   // n -> tw2 | tw3 | twr (one allocation)
   // host-buffer pipeline
   cudaStream_t h2d = nullptr, d2h = nullptr;
   static constexpr int kSlots = 3;
@@ -121,6 +126,84 @@ int launch_cfg(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
   return SA_OK;
 }
 
+// ---- tuned family (N = 1024..8192) ----------------------------------------------------------------
+template <class C>
+int get_v2_tables(sa_ctx *ctx, V2Params &P) {
+  auto it = ctx->v2_tables.find(C::N);
+  if (it == ctx->v2_tables.end()) {
+    const std::vector<float> w = sa_host::twiddle_table(C::N);  // W_N[i], i < N
+    std::vector<float> host(2 * (size_t)(C::NTW2 + C::NTW3 + C::NTWR));
+    size_t o = 0;
+    auto put = [&](size_t idx) { host[o++] = w[2 * idx]; host[o++] = w[2 * idx + 1]; };
+    for (int k = 1; k < 16; k++)                       // pass 2: w_256^(k p) = W_N[k p N/256]
+      for (int pp = 0; pp < 16; pp++) put((size_t)k * pp * (C::N / 256));
+    for (int k = 1; k < C::R3; k++)                    // pass 3: w_M^(k p) = W_N[2 k p]
+      for (int pp = 0; pp < 256; pp++) put((size_t)2 * k * pp);
+    for (int k = 0; k < C::NTWR; k++) put((size_t)k);  // recombination: W_N^k
+    float2 *dev = nullptr;
+    SA_CUDA(cudaMalloc(&dev, host.size() * sizeof(float)));
+    SA_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->v2_tables.emplace(C::N, dev).first;
+  }
+  P.tw2 = it->second;
+  P.tw3 = P.tw2 + C::NTW2;
+  P.twr = P.tw3 + C::NTW3;
+  return SA_OK;
+}
+
+template <class C, int MODE, bool FULL>
+int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
+  KernelPlan &plan = ctx->plans_v2[C::LOG2N][MODE][FULL ? 1 : 0];
+  auto kernel = spectrum_kernel_v2<C, MODE, FULL>;
+  if (!plan.ready) {
+    SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TOTAL));
+    int per_sm = 0;
+    SA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::NT, C::SMEM_TOTAL));
+    if (per_sm < 1) { g_last_error = "v2 kernel does not fit on an SM"; return SA_ERR_CUDA; }
+    plan.max_blocks = per_sm * ctx->num_sms;
+    plan.ready = true;
+  }
+  const u64 needed = (P.b.n_frames + C::G - 1) / C::G;
+  const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
+  kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(P);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+template <class C>
+int launch_v2(sa_ctx *ctx, const SpectrumParams &p) {
+  V2Params P;
+  P.b = p;
+  int e = get_v2_tables<C>(ctx, P);
+  if (e != SA_OK) return e;
+  const bool full = p.bin_lo == 0 && p.bin_hi == (uint32_t)C::M;
+  int mode = SCALE_MUL;
+  P.cmul = 0.5f;
+  P.div = 1.0f;
+  P.rdiv = 1.0f;
+  switch (p.scaling_kind) {
+    case SA_SCALING_NONE: break;
+    case SA_SCALING_DIVIDE_BY_N: P.cmul = 0.5f / (float)C::N; break;                  // exact: N = 2^k
+    case SA_SCALING_DIVIDE_BY_N_SQRT:
+      if (C::LOG2N % 2 == 0) P.cmul = 0.5f / p.scale_div;                              // sqrt(N) = 2^(k/2), exact
+      else { mode = SCALE_DIV; P.div = p.scale_div; P.rdiv = 1.0f / p.scale_div; }
+      break;
+    case SA_SCALING_ZERO_TO_ONE: mode = SCALE_ZERO_ONE; break;
+    default: mode = SCALE_LOG10; break;
+  }
+#define SA_V2_CASE(M_) \
+  case M_: return full ? launch_v2_inst<C, M_, true>(ctx, P) : launch_v2_inst<C, M_, false>(ctx, P);
+  switch (mode) {
+    SA_V2_CASE(SCALE_MUL)
+    SA_V2_CASE(SCALE_DIV)
+    SA_V2_CASE(SCALE_ZERO_ONE)
+    default: return full ? launch_v2_inst<C, SCALE_LOG10, true>(ctx, P) : launch_v2_inst<C, SCALE_LOG10, false>(ctx, P);
+  }
+#undef SA_V2_CASE
+}
+
 int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
   if (p.n_frames == 0) return SA_OK;
   switch (log2n) {
@@ -135,10 +218,10 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 7: return launch_cfg<SpectrumCfg<7, 8, 16>>(ctx, p, log2n);
     case 8: return launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n);
     case 9: return launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n);
-    case 10: return launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n);
-    case 11: return launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n);
-    case 12: return launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n);
-    case 13: return launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n);
+    case 10: return ctx->use_generic ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, 16>>(ctx, p);
+    case 11: return ctx->use_generic ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
+    case 12: return ctx->use_generic ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
+    case 13: return ctx->use_generic ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
     case 14: return launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n);
     case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
     default: return SA_ERR_UNSUPPORTED_LENGTH;
@@ -285,6 +368,8 @@ int sa_ctx_create_on_stream(int device, void *cuda_stream, sa_ctx **out_ctx) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  const char *fg = getenv("SA_FORCE_GENERIC");
+  ctx->use_generic = fg && fg[0] == '1';
   *out_ctx = ctx;
   return SA_OK;
 }
@@ -306,6 +391,7 @@ int sa_ctx_destroy(sa_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->twiddles) cudaFree(kv.second);
   for (auto &kv : ctx->windows) cudaFree(kv.second);
+  for (auto &kv : ctx->v2_tables) cudaFree(kv.second);
   for (int s = 0; s < sa_ctx::kSlots; s++) {
     cudaFree(ctx->slot_in[s]); cudaFree(ctx->slot_out[s]); cudaFree(ctx->slot_stats[s]);
     if (ctx->pipeline_ready) { cudaEventDestroy(ctx->ev_h2d[s]); cudaEventDestroy(ctx->ev_comp[s]); cudaEventDestroy(ctx->ev_d2h[s]); }

@@ -1,0 +1,576 @@
+// sa_spectrum_v2.cuh -- tuned fused kernel family for N in {1024, 2048, 4096, 8192} (T = N/32
+// threads per frame, a multiple of the warp size).
+//
+// Same math and same outputs as sa_spectrum_kernel.cuh (the generic family), restructured around
+// what the v1 ncu profile showed (profiles/r01_v1_summary.md): the kernel is instruction- and
+// latency-bound, DRAM traffic already equals the algorithmic bytes.
+//
+//  * CTA = G independent frame groups of T threads (G*T = 512): each group walks its own frames and
+//    synchronises with its own named barrier (bar.sync id, T), so groups overlap each other's
+//    barrier/latency phases; 16 warps/SM at <= 128 registers.
+//  * read-only tables live once per CTA in shared memory: window multipliers (src/windows.rs),
+//    per-pass twiddles laid out [k][p] (conflict-free / broadcast), recombination twiddles.
+//  * two exchange buffers per group, alternated on every exchange: one barrier per exchange.
+//  * next frame's samples are requested (ld.global.nc) right after the recombination, so their
+//    latency hides behind the statistics phase; the window multiply happens when they are consumed.
+//  * magnitude = sqrt.approx(|.|^2) * c, where c folds the real-FFT 1/2 and a power-of-two scaling
+//    divisor (divide_by_N always, divide_by_N_sqrt when log2 N is even) into one exact multiply;
+//    other divisors use an exactly-rounded FMA division.
+//  * statistics: u32 min/max on the value bit patterns (3-input VIMNMX), redux.sync across the warp,
+//    arg-bins resolved only by the threads that hold the extreme value (stable-sort tie rules of
+//    src/spectrum.rs:496-499,529-530 via atomicMin / atomicMax on the bin index).
+//  * NaN/Inf validation (src/lib.rs:168-173) costs nothing on clean frames: any non-finite input
+//    makes every output bin non-finite, so the maximum flags it and only then the group re-reads
+//    its samples to classify NaN vs Inf vs overflow.
+//  * median (src/spectrum.rs:515-524): exact selection by one histogram pass over up to 1024
+//    buckets spanning [min,max] of the value bit patterns, a block scan, compaction of the
+//    (typically < 8) candidates of the selected bucket and a warp-level rank count; degenerate
+//    distributions iterate the same pass on the narrowed range.
+#pragma once
+#include "sa_common.cuh"
+#include "sa_dft.cuh"
+
+namespace sa {
+
+enum ScaleMode { SCALE_MUL = 0, SCALE_DIV = 1, SCALE_ZERO_ONE = 2, SCALE_LOG10 = 3 };
+
+struct V2Params {
+  SpectrumParams b;
+  const float2 *tw2;   // [15][16]           w_256^(k*p)
+  const float2 *tw3;   // [R3-1][256]        w_M^(k*p)
+  const float2 *twr;   // [M/2]              W_N^k  (recombination)
+  float cmul;          // SCALE_MUL: 0.5/div (exact power of two); else 0.5
+  float div;           // SCALE_DIV: divisor d
+  float rdiv;          // SCALE_DIV: RN(1/d)
+};
+
+template <int LOG2N_, int G_>
+struct V2Cfg {
+  static constexpr int LOG2N = LOG2N_, N = 1 << LOG2N_, M = N / 2, E = 16, T = M / E, G = G_, NT = T * G_;
+  static constexpr int NW = T / 32;                  // warps per group
+  static constexpr int R3 = M / 256;                 // radix of the last pass (2, 4, 8 or 16)
+  static constexpr int NB3 = 16 / R3;                // butterflies per thread in the last pass
+  static constexpr int BUF = M + M / 16;             // padded float2 elements of one exchange buffer
+  static constexpr int NBUCKET = (8 * T < 1024) ? 8 * T : 1024;
+  static constexpr int BPT = NBUCKET / T;            // histogram buckets scanned per thread
+  static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2;
+  static_assert(T % 32 == 0 && T >= 32 && T <= 256, "v2 covers N = 1024..8192");
+  static_assert(NT <= 1024 && (T == 32 || G_ <= 15), "named barriers 1..15");
+  // shared memory map (bytes)
+  static constexpr size_t OFF_WIN = 0;
+  static constexpr size_t OFF_TW2 = OFF_WIN + sizeof(float) * N;
+  static constexpr size_t OFF_TW3 = OFF_TW2 + sizeof(float2) * NTW2;
+  static constexpr size_t OFF_TWR = OFF_TW3 + sizeof(float2) * NTW3;
+  static constexpr size_t OFF_GROUPS = OFF_TWR + sizeof(float2) * NTWR;
+  static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
+  static constexpr size_t G_HIST = sizeof(uint32_t) * (NBUCKET + 8);
+  static constexpr size_t G_MISC = sizeof(uint32_t) * 64;
+  static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
+  static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST;
+  static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
+};
+
+// misc words of a group
+enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_WTOT = 24, MI_ARGMIN = 32, MI_ARGMAX = 33, MI_LCOUNT = 34,
+       MI_SELA = 36 /*b, below, cnt*/, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45, MI_FLAGS = 46, MI_UMAX = 48 };
+
+template <int T>
+__device__ __forceinline__ void group_sync(int g) {
+  if constexpr (T == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// keys: order-preserving u32 image of a value.  All modes except 20*log10 produce non-negative
+// values whose raw bit pattern is already ordered.
+template <int MODE>
+__device__ __forceinline__ uint32_t v2_key(float v) {
+  if constexpr (MODE == SCALE_LOG10) return ordered_key(v);
+  else return __float_as_uint(v);
+}
+template <int MODE>
+__device__ __forceinline__ float v2_unkey(uint32_t k) {
+  if constexpr (MODE == SCALE_LOG10) return key_to_float(k);
+  else return __uint_as_float(k);
+}
+
+// Exactly-rounded v/d for a launch-constant d (rd = RN(1/d)): q = RN(v*rd), r = v - q*d (exact, FMA),
+// q' = RN(q + r*rd) (Markstein).  Used for divide_by_N_sqrt with odd log2 N (d = 2^k * sqrt(2)).
+__device__ __forceinline__ float div_const(float v, float d, float rd) {
+  const float q = v * rd;
+  const float r = fmaf(-q, d, v);
+  return fmaf(r, rd, q);
+}
+
+template <class C, int MODE, bool FULL>
+__global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P) {
+  constexpr int N = C::N, M = C::M, E = C::E, T = C::T, G = C::G, NW = C::NW, R3 = C::R3, NB3 = C::NB3;
+  constexpr int PADT = T + T / 16;  // padded stride of the strided reads
+  extern __shared__ __align__(16) unsigned char smem[];
+  float *s_win = reinterpret_cast<float *>(smem + C::OFF_WIN);
+  float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);
+  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + C::OFF_TW3);
+  float2 *s_twr = reinterpret_cast<float2 *>(smem + C::OFF_TWR);
+
+  const SpectrumParams &p = P.b;
+  const int tid = threadIdx.x;
+  const int g = tid / T, j = tid - g * T;
+  const int lane = tid & 31, wig = j >> 5;  // warp index inside the group
+  unsigned char *gbase = smem + C::OFF_GROUPS + (size_t)g * C::G_BYTES;
+  float2 *bufA = reinterpret_cast<float2 *>(gbase);
+  float2 *bufB = reinterpret_cast<float2 *>(gbase + C::G_BUF);
+  uint32_t *hist = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
+  uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
+  uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
+
+  // ---- one-time: tables -> shared memory, histogram cleared ------------------------------------
+  const bool has_win = p.window != nullptr;
+  for (int i = tid; i < N; i += C::NT) s_win[i] = has_win ? __ldg(p.window + i) : 1.0f;
+  for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
+  for (int i = tid; i < C::NTW3; i += C::NT) s_tw3[i] = __ldg(P.tw3 + i);
+  for (int i = tid; i < C::NTWR; i += C::NT) s_twr[i] = __ldg(P.twr + i);
+  for (int i = j; i < C::NBUCKET + 8; i += T) hist[i] = 0;
+  __syncthreads();
+
+  const uint32_t lo = p.bin_lo, hi = p.bin_hi;
+  const uint32_t count = hi - lo + 1;
+  const bool want_stats = p.stats != nullptr;
+  const bool want_median = want_stats && (p.stats_mask & SA_STATS_MEDIAN);
+  const float cscale = P.cmul;
+
+  u64 frame = (u64)blockIdx.x * G + g;
+  const u64 fstep = (u64)gridDim.x * G;
+  if (frame >= p.n_frames) return;  // group-uniform; no CTA-wide barrier after this point
+
+  // ---- load of the first frame (raw samples; the window is applied at the top of the loop) ------
+  float2 x[E];
+  {
+    const float *src = p.samples + frame * p.frame_stride;
+#pragma unroll
+    for (int s = 0; s < E; s++) {
+      const int n = j + s * T;
+      if (p.aligned8) x[s] = __ldg(reinterpret_cast<const float2 *>(src) + n);
+      else { x[s].x = __ldg(src + 2 * n); x[s].y = __ldg(src + 2 * n + 1); }
+    }
+  }
+  float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
+
+#pragma unroll 1
+  for (;;) {
+    if (j == 0) { misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_LCOUNT] = 0u; misc[MI_FLAGS] = 0u; }
+
+    // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
+#pragma unroll
+    for (int s = 0; s < E; s++) {
+      const float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * (j + s * T));
+      x[s].x = __fmul_rn(w.x, x[s].x);
+      x[s].y = __fmul_rn(w.y, x[s].y);
+    }
+
+    // ---- pass 1: radix 16, NS = 1 (no twiddles) -------------------------------------------------
+    dft16(x);
+    {
+      float2 *w = wbuf + 17 * j;  // pad(16 j + k) = 17 j + k
+#pragma unroll
+      for (int k = 0; k < 16; k++) w[k] = x[k];
+    }
+    group_sync<T>(g);
+    {
+      const float2 *r = wbuf + (j + (j >> 4));
+#pragma unroll
+      for (int s = 0; s < 16; s++) x[s] = r[s * PADT];
+    }
+    { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+
+    // ---- pass 2: radix 16, NS = 16 ---------------------------------------------------------------
+    {
+      const int pp = j & 15;
+#pragma unroll
+      for (int k = 1; k < 16; k++) x[k] = cmul(x[k], s_tw2[(k - 1) * 16 + pp]);
+    }
+    dft16(x);
+    {
+      // logical index (j/16)*256 + (j%16) + 16 k  ->  padded (j/16)*272 + (j%16) + 17 k
+      float2 *w = wbuf + (j >> 4) * 272 + (j & 15);
+#pragma unroll
+      for (int k = 0; k < 16; k++) w[17 * k] = x[k];
+    }
+    group_sync<T>(g);
+    {
+      const float2 *r = wbuf + (j + (j >> 4));
+#pragma unroll
+      for (int s = 0; s < 16; s++) x[s] = r[s * PADT];
+    }
+    { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+
+    // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
+#pragma unroll
+    for (int b = 0; b < NB3; b++) {
+      float2 v[R3];
+#pragma unroll
+      for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
+      const int jb = j + b * T;  // < 256
+#pragma unroll
+      for (int k = 1; k < R3; k++) v[k] = cmul(v[k], s_tw3[(k - 1) * 256 + jb]);
+      dft<R3>(v);
+#pragma unroll
+      for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
+    }
+
+    // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
+    // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
+    {
+      float2 *w = wbuf + (j + (j >> 4));
+#pragma unroll
+      for (int s = E / 2; s < E; s++) w[(s - E / 2) * PADT] = x[s];
+    }
+    group_sync<T>(g);
+    float val[E];        // val[2s] = bin j + s*T, val[2s+1] = bin M - (j + s*T); (j,s)=(0,0): bins 0 and M
+    float vmid = 0.f;    // bin M/2, thread 0 only
+    {
+      // partner of k = j + s*T sits at index M/2 - k of the upper-half buffer; T % 16 == 0, so the
+      // padded address is pad(M/2 - j) - s*PADT
+      const int base = M / 2 - j;
+      const float2 *r = wbuf + (base + (base >> 4));
+#pragma unroll
+      for (int s = 0; s < E / 2; s++) {
+        const float2 a = x[s];
+        const float2 bq = r[-s * PADT];
+        const float2 w = s_twr[j + s * T];
+        const float pr = a.x + bq.x, pi = a.y - bq.y;
+        const float qr = a.x - bq.x, qi = a.y + bq.y;
+        const float tr = fmaf(w.x, qi, w.y * qr);
+        const float ti = fmaf(w.y, qi, -(w.x * qr));
+        const float ur = pr + tr, ui = pi + ti;
+        const float vr = pr - tr, vi = pi - ti;
+        val[2 * s] = sqrt_approx(fmaf(ur, ur, ui * ui));
+        val[2 * s + 1] = sqrt_approx(fmaf(vr, vr, vi * vi));
+      }
+      if (j == 0) {
+        // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
+        const float2 z0 = x[0];
+        const float2 zm = wbuf[0];
+        val[0] = 2.0f * fabsf(z0.x + z0.y);                      // X[0]   = Zr + Zi
+        val[1] = 2.0f * fabsf(z0.x - z0.y);                      // X[N/2] = Zr - Zi (packed Nyquist)
+        vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
+      }
+    }
+    { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+
+    // ---- request the next frame now; its latency hides behind the statistics phase ---------------
+    const u64 cur = frame;
+    frame += fstep;
+    const bool more = frame < p.n_frames;
+    if (more) {
+      const float *src = p.samples + frame * p.frame_stride;
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+        const int n = j + s * T;
+        if (p.aligned8) x[s] = __ldg(reinterpret_cast<const float2 *>(src) + n);
+        else { x[s].x = __ldg(src + 2 * n); x[s].y = __ldg(src + 2 * n + 1); }
+      }
+    }
+
+    // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
+    uint32_t valid = 0xffffffffu;
+    bool valid_mid = (j == 0);
+    if constexpr (!FULL) {
+      valid = 0;
+#pragma unroll
+      for (int s = 0; s < E / 2; s++) {
+        const uint32_t k0 = (j == 0 && s == 0) ? 0u : (uint32_t)(j + s * T);
+        const uint32_t k1 = (uint32_t)M - (uint32_t)(j + s * T);
+        valid |= (k0 >= lo && k0 <= hi) ? (1u << (2 * s)) : 0u;
+        valid |= (k1 >= lo && k1 <= hi) ? (2u << (2 * s)) : 0u;
+      }
+      valid_mid = valid_mid && ((uint32_t)(M / 2) >= lo && (uint32_t)(M / 2) <= hi);
+    }
+#define SA_VALID(i) (FULL || ((valid >> (i)) & 1u))
+
+    // ---- unscaled values u = 0.5*sqrt(..) and, for the modes that need it, max|u| ----------------
+    float umax = 0.f;
+    if constexpr (MODE == SCALE_ZERO_ONE || MODE == SCALE_LOG10) {
+      uint32_t ub = 0;
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        val[i] *= 0.5f;
+        if (SA_VALID(i)) ub = max(ub, __float_as_uint(val[i]) & 0x7fffffffu);
+      }
+      vmid *= 0.5f;
+      if (valid_mid) ub = max(ub, __float_as_uint(vmid) & 0x7fffffffu);
+      ub = __reduce_max_sync(0xffffffffu, ub);
+      if constexpr (NW > 1) {
+        if (lane == 0) misc[MI_UMAX + wig] = ub;
+        group_sync<T>(g);
+#pragma unroll
+        for (int w = 0; w < NW; w++) ub = max(ub, misc[MI_UMAX + w]);
+      }
+      umax = __uint_as_float(ub);
+    }
+
+    // ---- scaling (src/scaling.rs:104-162) ---------------------------------------------------------
+    auto scale1 = [&](float v) -> float {
+      if constexpr (MODE == SCALE_MUL) return v * cscale;                                    // exact
+      else if constexpr (MODE == SCALE_DIV) return div_const(v * 0.5f, P.div, P.rdiv);
+      else if constexpr (MODE == SCALE_ZERO_ONE) return umax != 0.0f ? __fdiv_rn(v, umax) : 0.0f;
+      else return (v == 0.0f) ? 0.0f : __fmul_rn(20.0f, log10f_musl(v));
+    };
+#pragma unroll
+    for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
+    vmid = scale1(vmid);
+
+    // ---- store the surviving bins ------------------------------------------------------------------
+    {
+      float *dst = p.out_vals + cur * p.out_stride - lo;
+#pragma unroll
+      for (int s = 0; s < E / 2; s++) {
+        const int k = j + s * T;
+        if (j == 0 && s == 0) {
+          if (SA_VALID(0)) dst[0] = val[0];
+          if (SA_VALID(1)) dst[M] = val[1];
+        } else {
+          if (SA_VALID(2 * s)) dst[k] = val[2 * s];
+          if (SA_VALID(2 * s + 1)) dst[M - k] = val[2 * s + 1];
+        }
+      }
+      if (valid_mid) dst[M / 2] = vmid;
+    }
+
+    // ---- statistics of the scaled values (src/spectrum.rs:481-539) --------------------------------
+    if (want_stats) {
+      uint32_t kmn = 0xffffffffu, kmx = 0u;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < E; i++) {
+        if (SA_VALID(i)) {
+          const uint32_t k = v2_key<MODE>(val[i]);
+          kmn = min(kmn, k);
+          kmx = max(kmx, k);
+          sum += val[i];
+        }
+      }
+      if (valid_mid) {
+        const uint32_t k = v2_key<MODE>(vmid);
+        kmn = min(kmn, k);
+        kmx = max(kmx, k);
+        sum += vmid;
+      }
+      const uint32_t my_kmn = kmn, my_kmx = kmx;
+      kmn = __reduce_min_sync(0xffffffffu, kmn);
+      kmx = __reduce_max_sync(0xffffffffu, kmx);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      if constexpr (NW > 1) {
+        if (lane == 0) { misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum); }
+        group_sync<T>(g);
+        kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
+#pragma unroll
+        for (int w = 1; w < NW; w++) {
+          kmn = min(kmn, misc[MI_KMIN + w]);
+          kmx = max(kmx, misc[MI_KMAX + w]);
+          sum += __uint_as_float(misc[MI_SUM + w]);
+        }
+      } else {
+        __syncwarp();
+      }
+      // arg bins: only threads that hold the extreme value search (min -> lowest bin, max -> highest)
+      if (my_kmn == kmn) {
+        uint32_t best = 0xffffffffu;
+#pragma unroll
+        for (int s = 0; s < E / 2; s++) {
+          const uint32_t k0 = (j == 0 && s == 0) ? 0u : (uint32_t)(j + s * T);
+          const uint32_t k1 = (uint32_t)M - (uint32_t)(j + s * T);
+          if (SA_VALID(2 * s) && v2_key<MODE>(val[2 * s]) == kmn) best = min(best, k0);
+          if (SA_VALID(2 * s + 1) && v2_key<MODE>(val[2 * s + 1]) == kmn) best = min(best, k1);
+        }
+        if (valid_mid && v2_key<MODE>(vmid) == kmn) best = min(best, (uint32_t)(M / 2));
+        atomicMin(&misc[MI_ARGMIN], best);
+      }
+      if (my_kmx == kmx) {
+        uint32_t best = 0u;
+#pragma unroll
+        for (int s = 0; s < E / 2; s++) {
+          const uint32_t k0 = (j == 0 && s == 0) ? 0u : (uint32_t)(j + s * T);
+          const uint32_t k1 = (uint32_t)M - (uint32_t)(j + s * T);
+          if (SA_VALID(2 * s) && v2_key<MODE>(val[2 * s]) == kmx) best = max(best, k0);
+          if (SA_VALID(2 * s + 1) && v2_key<MODE>(val[2 * s + 1]) == kmx) best = max(best, k1);
+        }
+        if (valid_mid && v2_key<MODE>(vmid) == kmx) best = max(best, (uint32_t)(M / 2));
+        atomicMax(&misc[MI_ARGMAX], best);
+      }
+
+      // non-finite spectrum value?  (keys of NaN/Inf sit above every finite key in all modes
+      // except 20*log10, which checks the unscaled maximum)
+      bool nonfinite;
+      if constexpr (MODE == SCALE_LOG10 || MODE == SCALE_ZERO_ONE) nonfinite = (__float_as_uint(umax) >= 0x7f800000u);
+      else nonfinite = (kmx >= 0x7f800000u);
+      if (nonfinite) {  // group-uniform rare path: classify NaN / Inf in the windowed input
+        const float *src = p.samples + cur * p.frame_stride;
+        uint32_t f = 4u;
+        for (int n = j; n < N; n += T) {
+          const float v = __fmul_rn(s_win[n], __ldg(src + n));
+          if (v != v) f |= 1u;
+          if (fabsf(v) == INFINITY) f |= 2u;
+        }
+        atomicOr(&misc[MI_FLAGS], f);
+      }
+
+      // ---- median: exact selection -----------------------------------------------------------------
+      uint32_t ka = kmn, kb = kmn;
+      if (want_median && kmx != kmn) {
+        const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;
+        uint32_t klo = kmn, width = kmx - kmn;     // candidates: keys with (key - klo) <= width
+        uint32_t rka = ra, rkb = rb;                // ranks relative to the candidate set
+#pragma unroll 1
+        for (;;) {
+          const int sh = max(0, (32 - __clz(width)) - (C::NBUCKET == 1024 ? 10 : (C::NBUCKET == 512 ? 9 : 8)));
+          // histogram of the candidates
+#pragma unroll
+          for (int i = 0; i < E; i++) {
+            const uint32_t t = v2_key<MODE>(val[i]) - klo;
+            if (SA_VALID(i) && t <= width) atomicAdd(&hist[t >> sh], 1u);
+          }
+          if (valid_mid) {
+            const uint32_t t = v2_key<MODE>(vmid) - klo;
+            if (t <= width) atomicAdd(&hist[t >> sh], 1u);
+          }
+          group_sync<T>(g);
+          // scan: BPT buckets per thread, warp inclusive scan, warp totals
+          uint32_t hb[C::BPT];
+          uint32_t local = 0;
+#pragma unroll
+          for (int b = 0; b < C::BPT; b++) { hb[b] = hist[j * C::BPT + b]; local += hb[b]; }
+#pragma unroll
+          for (int b = 0; b < C::BPT; b++) hist[j * C::BPT + b] = 0;
+          uint32_t incl = local;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+          }
+          if constexpr (NW > 1) {
+            if (lane == 31) misc[MI_WTOT + wig] = incl;
+            group_sync<T>(g);
+#pragma unroll
+            for (int w = 0; w < NW; w++) if (w < wig) incl += misc[MI_WTOT + w];
+          }
+          const uint32_t excl = incl - local;
+          if (excl <= rka && rka < incl) {
+            uint32_t c = excl;
+#pragma unroll
+            for (int b = 0; b < C::BPT; b++) {
+              if (rka >= c && rka < c + hb[b]) { misc[MI_SELA] = j * C::BPT + b; misc[MI_SELA + 1] = c; misc[MI_SELA + 2] = hb[b]; }
+              c += hb[b];
+            }
+          }
+          if (excl <= rkb && rkb < incl) {
+            uint32_t c = excl;
+#pragma unroll
+            for (int b = 0; b < C::BPT; b++) {
+              if (rkb >= c && rkb < c + hb[b]) { misc[MI_SELB] = j * C::BPT + b; misc[MI_SELB + 1] = c; misc[MI_SELB + 2] = hb[b]; }
+              c += hb[b];
+            }
+          }
+          group_sync<T>(g);
+          const uint32_t ba = misc[MI_SELA], below_a = misc[MI_SELA + 1], cnt_a = misc[MI_SELA + 2];
+          const uint32_t bb = misc[MI_SELB];
+          if (sh == 0) {  // buckets are single keys
+            ka = klo + ba;
+            kb = klo + bb;
+            break;
+          }
+          const uint32_t lo_a = klo + (ba << sh), lo_b = klo + (bb << sh), bw = (1u << sh) - 1u;
+          if (ba != bb) {
+            // the two middle ranks fall into different buckets: s[ra] is the largest key of bucket a,
+            // s[rb] the smallest key of bucket b
+            uint32_t ma = 0u, mb = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+              const uint32_t k = v2_key<MODE>(val[i]);
+              if (SA_VALID(i) && (k - lo_a) <= bw) ma = max(ma, k);
+              if (SA_VALID(i) && (k - lo_b) <= bw) mb = min(mb, k);
+            }
+            if (valid_mid) {
+              const uint32_t k = v2_key<MODE>(vmid);
+              if ((k - lo_a) <= bw) ma = max(ma, k);
+              if ((k - lo_b) <= bw) mb = min(mb, k);
+            }
+            ma = __reduce_max_sync(0xffffffffu, ma);
+            mb = __reduce_min_sync(0xffffffffu, mb);
+            if (j == 0) { misc[MI_RESA] = 0u; misc[MI_RESB] = 0xffffffffu; }
+            group_sync<T>(g);
+            if (lane == 0) { atomicMax(&misc[MI_RESA], ma); atomicMin(&misc[MI_RESB], mb); }
+            group_sync<T>(g);
+            ka = misc[MI_RESA];
+            kb = misc[MI_RESB];
+            break;
+          }
+          if (cnt_a <= 32) {
+            // compaction of the selected bucket + warp-level rank count
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+              const uint32_t k = v2_key<MODE>(val[i]);
+              if (SA_VALID(i) && (k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u)] = k;
+            }
+            if (valid_mid) {
+              const uint32_t k = v2_key<MODE>(vmid);
+              if ((k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u)] = k;
+            }
+            group_sync<T>(g);
+            if (wig == 0) {
+              const uint32_t mine = (lane < cnt_a) ? list[lane] : 0xffffffffu;
+              uint32_t rank = 0;
+              for (uint32_t c = 0; c < cnt_a; c++) {
+                const uint32_t o = __shfl_sync(0xffffffffu, mine, c);
+                rank += (o < mine || (o == mine && c < (uint32_t)lane)) ? 1u : 0u;
+              }
+              const uint32_t wa = rka - below_a, wb = rkb - below_a;
+              const uint32_t ma = __ballot_sync(0xffffffffu, lane < cnt_a && rank == wa);
+              const uint32_t mb = __ballot_sync(0xffffffffu, lane < cnt_a && rank == wb);
+              ka = __shfl_sync(0xffffffffu, mine, __ffs(ma) - 1);
+              kb = __shfl_sync(0xffffffffu, mine, __ffs(mb) - 1);
+              if (lane == 0) misc[MI_LCOUNT] = 0u;
+            }
+            break;  // only warp 0 (thread 0 writes the record) holds ka/kb; others do not need them
+          }
+          // crowded bucket (many near-equal values): narrow the candidate set and repeat
+          klo = lo_a;
+          width = bw;
+          rka -= below_a;
+          rkb -= below_a;
+        }
+      }
+
+      group_sync<T>(g);  // arg bins / flags complete
+      if (j == 0) {
+        const bool mm = p.stats_mask & SA_STATS_MINMAX;
+        uint4 r0, r1;
+        r0.x = mm ? __float_as_uint(v2_unkey<MODE>(kmn)) : 0u;
+        r0.y = mm ? misc[MI_ARGMIN] : 0u;
+        r0.z = mm ? __float_as_uint(v2_unkey<MODE>(kmx)) : 0u;
+        r0.w = mm ? misc[MI_ARGMAX] : 0u;
+        r1.x = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(sum, (float)count)) : 0u;
+        float med = 0.f;
+        if (want_median)
+          med = (count & 1u) ? v2_unkey<MODE>(kb)
+                             : __fdiv_rn(__fadd_rn(v2_unkey<MODE>(ka), v2_unkey<MODE>(kb)), 2.0f);
+        r1.y = __float_as_uint(med);
+        const uint32_t fl = misc[MI_FLAGS];
+        r1.z = (fl & 1u) ? SA_ERR_NAN_VALUES : (fl & 2u) ? SA_ERR_INFINITY_VALUES : (fl & 4u) ? SA_ERR_NON_FINITE_RESULT : SA_OK;
+        r1.w = 0u;
+        uint4 *rec = reinterpret_cast<uint4 *>(&p.stats[cur]);
+        rec[0] = r0;
+        rec[1] = r1;
+      }
+    }
+#undef SA_VALID
+    if (!more) break;
+  }
+}
+
+}  // namespace sa
