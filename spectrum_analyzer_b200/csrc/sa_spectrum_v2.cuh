@@ -153,9 +153,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     const float *src = p.samples + frame * p.frame_stride;
 #pragma unroll
     for (int s = 0; s < E; s++) {
-      const int n = j + s * T;
-      if (p.aligned8) x[s] = __ldg(reinterpret_cast<const float2 *>(src) + n);
-      else { x[s].x = __ldg(src + 2 * n); x[s].y = __ldg(src + 2 * n + 1); }
+      x[s] = __ldg(reinterpret_cast<const float2 *>(src) + (j + s * T));  // 8-byte aligned (host checks)
     }
   }
   float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
@@ -168,8 +166,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 #pragma unroll
     for (int s = 0; s < E; s++) {
       const float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * (j + s * T));
-      x[s].x = __fmul_rn(w.x, x[s].x);
-      x[s].y = __fmul_rn(w.y, x[s].y);
+      x[s] = mul2(w, x[s]);  // two exact IEEE multiplies
     }
 
     // ---- pass 1: radix 16, NS = 1 (no twiddles) -------------------------------------------------
@@ -242,14 +239,13 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         const float2 a = x[s];
         const float2 bq = r[-s * PADT];
         const float2 w = s_twr[j + s * T];
-        const float pr = a.x + bq.x, pi = a.y - bq.y;
-        const float qr = a.x - bq.x, qi = a.y + bq.y;
-        const float tr = fmaf(w.x, qi, w.y * qr);
-        const float ti = fmaf(w.y, qi, -(w.x * qr));
-        const float ur = pr + tr, ui = pi + ti;
-        const float vr = pr - tr, vi = pi - ti;
-        val[2 * s] = sqrt_approx(fmaf(ur, ur, ui * ui));
-        val[2 * s + 1] = sqrt_approx(fmaf(vr, vr, vi * vi));
+        // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
+        const float2 cb = make_float2(bq.x, -bq.y);
+        const float2 pp = add2(a, cb), qq = sub2(a, cb);
+        const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
+        const float2 uu = add2(pp, tt), vv = sub2(pp, tt);
+        val[2 * s] = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
+        val[2 * s + 1] = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
       }
       if (j == 0) {
         // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
@@ -269,11 +265,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     if (more) {
       const float *src = p.samples + frame * p.frame_stride;
 #pragma unroll
-      for (int s = 0; s < E; s++) {
-        const int n = j + s * T;
-        if (p.aligned8) x[s] = __ldg(reinterpret_cast<const float2 *>(src) + n);
-        else { x[s].x = __ldg(src + 2 * n); x[s].y = __ldg(src + 2 * n + 1); }
-      }
+      for (int s = 0; s < E; s++) x[s] = __ldg(reinterpret_cast<const float2 *>(src) + (j + s * T));
     }
 
     // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
@@ -320,8 +312,17 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       else if constexpr (MODE == SCALE_ZERO_ONE) return umax != 0.0f ? __fdiv_rn(v, umax) : 0.0f;
       else return (v == 0.0f) ? 0.0f : __fmul_rn(20.0f, log10f_musl(v));
     };
+    if constexpr (MODE == SCALE_MUL) {
 #pragma unroll
-    for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
+      for (int i = 0; i < E; i += 2) {
+        const float2 r = mul2(make_float2(val[i], val[i + 1]), bcast2(cscale));
+        val[i] = r.x;
+        val[i + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
+    }
     vmid = scale1(vmid);
 
     // ---- store the surviving bins ------------------------------------------------------------------
@@ -422,7 +423,8 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
       // ---- median: exact selection -----------------------------------------------------------------
       uint32_t ka = kmn, kb = kmn;
-      if (want_median && kmx != kmn) {
+      const bool median_barriers = want_median && kmx != kmn;  // that path already orders the atomics above
+      if (median_barriers) {
         const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;
         uint32_t klo = kmn, width = kmx - kmn;     // candidates: keys with (key - klo) <= width
         uint32_t rka = ra, rkb = rb;                // ranks relative to the candidate set
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         }
       }
 
-      group_sync<T>(g);  // arg bins / flags complete
+      if (!median_barriers) group_sync<T>(g);  // arg bins / flags complete
       if (j == 0) {
         const bool mm = p.stats_mask & SA_STATS_MINMAX;
         uint4 r0, r1;
