@@ -138,8 +138,8 @@ inline void limit_bins(uint32_t n, uint32_t sampling_rate, int kind, float lo, f
     while (a < b) { const uint32_t m = a + (b - a) / 2; if (freq(m) > hi) b = m; else a = m + 1; }
     end = a;
   }
-  *bin_lo = first;
   *n_bins = end > first ? end - first : 0;
+  *bin_lo = *n_bins ? first : 0;
 }
 
 // W_N[i] = exp(-2*pi*i*i/N), i in [0, N): quarter-wave sine table in double, rounded to f32,

@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 #pragma unroll
     for (int s = 0; s < E; s++) {
       const float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * (j + s * T));
-      x[s] = mul2(w, x[s]);  // two exact IEEE multiplies
+      // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
+      // skip the rounding of the windowed sample that the reference performs (src/windows.rs:47)
+      x[s].x = __fmul_rn(w.x, x[s].x);
+      x[s].y = __fmul_rn(w.y, x[s].y);
     }
 
     // ---- pass 1: radix 16, NS = 1 (no twiddles) -------------------------------------------------
