@@ -188,6 +188,11 @@ int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint
 int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t n_frames, uint32_t n,
                       uint64_t frame_stride, float *d_out);
 
+/* Same with HOST buffers (drop-in for `windows::hann_window(&[f32]) -> Vec<f32>` etc.): H2D, the window
+ * kernel, D2H; synchronous.  h_out is dense [n_frames x n]. */
+int sa_window_host(sa_ctx *ctx, int window_kind, const float *h_in, uint64_t n_frames, uint32_t n,
+                   uint64_t frame_stride, float *h_out);
+
 /* Synthetic input: counter-based uniform noise in [-1,1) written on the device;
  * value i depends only on (seed, first_index + i) so the CPU checker can regenerate it. */
 int sa_generate_noise(sa_ctx *ctx, float *d_out, uint64_t first_index, uint64_t count, uint64_t seed);

@@ -446,19 +446,14 @@ def _window_apply(kind: int, samples, ctx: Context | None):
         if x.numel():
             _check(lib.sa_window_batched(c._h, kind, x.data_ptr(), frames, n, n, out.data_ptr()))
         return out
-    import torch
     x = np.ascontiguousarray(samples, dtype=np.float32)
     if x.size == 0:
         return x.copy()
     c = ctx or default_context()
-    dev = torch.device("cuda", c.device)
-    d_in = torch.from_numpy(x).to(dev)
-    d_out = torch.empty_like(d_in)
-    torch.cuda.synchronize(dev)
     n = x.shape[-1]
-    _check(lib.sa_window_batched(c._h, kind, d_in.data_ptr(), x.size // n, n, n, d_out.data_ptr()))
-    c.sync()
-    return d_out.cpu().numpy()
+    out = np.empty_like(x)
+    _check(lib.sa_window_host(c._h, kind, x.ctypes.data, x.size // n, n, n, out.ctypes.data))
+    return out
 
 
 class windows:  # namespace, like the crate's `windows` module

@@ -595,6 +595,28 @@ int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t 
   return SA_OK;
 }
 
+int sa_window_host(sa_ctx *ctx, int window_kind, const float *h_in, uint64_t n_frames, uint32_t n,
+                   uint64_t frame_stride, float *h_out) {
+  if (!ctx || !h_in || !h_out || n == 0 || n > 32768 || frame_stride == 0) return SA_ERR_INVALID_ARGUMENT;
+  if (window_kind < SA_WINDOW_NONE || window_kind > SA_WINDOW_BLACKMAN_HARRIS_7TERM) return SA_ERR_INVALID_ARGUMENT;
+  if (n_frames == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(ctx->device));
+  const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (std::max<uint64_t>(frame_stride, n) * sizeof(float)));
+  const uint64_t cf = std::min(chunk, n_frames);
+  int pe = ensure_pipeline(ctx, ((cf - 1) * frame_stride + n) * sizeof(float), cf * n * sizeof(float), 32);
+  if (pe != SA_OK) return pe;
+  for (uint64_t f0 = 0; f0 < n_frames; f0 += cf) {   // simple serial chunks: this is not the hot entry point
+    const uint64_t nf = std::min(cf, n_frames - f0);
+    SA_CUDA(cudaMemcpyAsync(ctx->slot_in[0], h_in + f0 * frame_stride, ((nf - 1) * frame_stride + n) * sizeof(float),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    pe = sa_window_batched(ctx, window_kind, ctx->slot_in[0], nf, n, frame_stride, ctx->slot_out[0]);
+    if (pe != SA_OK) return pe;
+    SA_CUDA(cudaMemcpyAsync(h_out + f0 * n, ctx->slot_out[0], nf * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SA_OK;
+}
+
 int sa_generate_noise(sa_ctx *ctx, float *d_out, uint64_t first_index, uint64_t count, uint64_t seed) {
   if (!ctx || (!d_out && count)) return SA_ERR_INVALID_ARGUMENT;
   if (count == 0) return SA_OK;
