@@ -51,8 +51,8 @@ struct V2Cfg {
   static constexpr int R3 = M / 256;                 // radix of the last pass (2, 4, 8 or 16)
   static constexpr int NB3 = 16 / R3;                // butterflies per thread in the last pass
   static constexpr int BUF = M + M / 16;             // padded float2 elements of one exchange buffer
-  static constexpr int NBUCKET = (8 * T < 1024) ? 8 * T : 1024;
-  static constexpr int BPT = NBUCKET / T;            // histogram buckets scanned per thread
+  static constexpr int HBITS = 8, NBUCKET = 1 << HBITS;   // median histogram: 256 buckets per pass
+  static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
   static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2;
   static_assert(T % 32 == 0 && T >= 32 && T <= 256, "v2 covers N = 1024..8192");
   static_assert(NT <= 1024 && (T == 32 || G_ <= 15), "named barriers 1..15");
@@ -71,8 +71,20 @@ struct V2Cfg {
 };
 
 // misc words of a group
-enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_WTOT = 24, MI_ARGMIN = 32, MI_ARGMAX = 33, MI_LCOUNT = 34,
-       MI_SELA = 36 /*b, below, cnt*/, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45, MI_FLAGS = 46, MI_UMAX = 48 };
+enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_CB = 24, MI_ARGMIN = 32, MI_ARGMAX = 33, MI_LCOUNT = 34,
+       MI_GUESS = 35, MI_SELA = 36 /*b, below, cnt*/, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45, MI_FLAGS = 46,
+       MI_UMAX = 48 };
+
+// predicated, branch-free shared-memory helpers (32-bit shared-window addresses)
+__device__ __forceinline__ void smem_inc_if(bool pred, uint32_t saddr) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.add.u32 [%1], 1; }" ::"r"((uint32_t)pred), "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void smem_push_if(bool pred, uint32_t key, uint32_t count_saddr, uint32_t list_saddr) {
+  asm volatile(
+      "{ .reg .pred p; .reg .u32 pos; setp.ne.u32 p, %0, 0; @p atom.shared.add.u32 pos, [%1], 1; "
+      "@p and.b32 pos, pos, 31; @p shl.b32 pos, pos, 2; @p add.u32 pos, pos, %2; @p st.shared.u32 [pos], %3; }" ::"r"((uint32_t)pred),
+      "r"(count_saddr), "r"(list_saddr), "r"(key) : "memory");
+}
 
 template <int T>
 __device__ __forceinline__ void group_sync(int g) {
@@ -127,6 +139,13 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   uint32_t *hist = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
   uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
   uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
+  const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+  const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(list);
+  const uint32_t lcount_s = (uint32_t)__cvta_generic_to_shared(misc + MI_LCOUNT);
+  constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
+  constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
+  uint32_t gw = 0u;                // 0: no guess yet (first frame of the group)
+  bool gw_next_known = false;
 
   // ---- one-time: tables -> shared memory, histogram cleared ------------------------------------
   const bool has_win = p.window != nullptr;
@@ -347,7 +366,17 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
     // ---- statistics of the scaled values (src/spectrum.rs:481-539) --------------------------------
     if (want_stats) {
-      uint32_t kmn = 0xffffffffu, kmx = 0u;
+      const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;   // middle ranks (0-based)
+      // Median window guess: keys within gw of the previous frame's median.  The fused pass below
+      // histograms only those and counts the keys under the window; the selection stays exact
+      // because the ranks are verified against the counts and the full-range pass is the fallback.
+      const bool use_win = want_median && gw != 0u;
+      const uint32_t gk = use_win ? misc[MI_GUESS] : 0u;
+      const uint32_t winL = gk > gw ? gk - gw : 0u;
+      const uint32_t winW = 2u * gw;
+      const int shw = max(0, (32 - __clz(winW | 1u)) - HBITS);
+
+      uint32_t kmn = 0xffffffffu, kmx = 0u, cb = 0u;
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < E; i++) {
@@ -364,20 +393,40 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         kmx = max(kmx, k);
         sum += vmid;
       }
+      if (use_win) {
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          const uint32_t k = v2_key<MODE>(val[i]);
+          const uint32_t t = k - winL;
+          cb += (SA_VALID(i) && k < winL) ? 1u : 0u;
+          smem_inc_if(SA_VALID(i) && t <= winW, hist_s + ((t >> shw) << 2));
+        }
+        if (valid_mid) {
+          const uint32_t k = v2_key<MODE>(vmid);
+          const uint32_t t = k - winL;
+          cb += (k < winL) ? 1u : 0u;
+          smem_inc_if(t <= winW, hist_s + ((t >> shw) << 2));
+        }
+      }
       const uint32_t my_kmn = kmn, my_kmx = kmx;
       kmn = __reduce_min_sync(0xffffffffu, kmn);
       kmx = __reduce_max_sync(0xffffffffu, kmx);
+      if (use_win) cb = __reduce_add_sync(0xffffffffu, cb);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
       if constexpr (NW > 1) {
-        if (lane == 0) { misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum); }
+        if (lane == 0) {
+          misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum);
+          misc[MI_CB + wig] = cb;
+        }
         group_sync<T>(g);
-        kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
+        kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]); cb = misc[MI_CB];
 #pragma unroll
         for (int w = 1; w < NW; w++) {
           kmn = min(kmn, misc[MI_KMIN + w]);
           kmx = max(kmx, misc[MI_KMAX + w]);
           sum += __uint_as_float(misc[MI_SUM + w]);
+          cb += misc[MI_CB + w];
         }
       } else {
         __syncwarp();
@@ -409,7 +458,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       }
 
       // non-finite spectrum value?  (keys of NaN/Inf sit above every finite key in all modes
-      // except 20*log10, which checks the unscaled maximum)
+      // except 20*log10 / zero-to-one, which check the unscaled maximum)
       bool nonfinite;
       if constexpr (MODE == SCALE_LOG10 || MODE == SCALE_ZERO_ONE) nonfinite = (__float_as_uint(umax) >= 0x7f800000u);
       else nonfinite = (kmx >= 0x7f800000u);
@@ -426,64 +475,67 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
       // ---- median: exact selection -----------------------------------------------------------------
       uint32_t ka = kmn, kb = kmn;
-      const bool median_barriers = want_median && kmx != kmn;  // that path already orders the atomics above
-      if (median_barriers) {
-        const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;
-        uint32_t klo = kmn, width = kmx - kmn;     // candidates: keys with (key - klo) <= width
-        uint32_t rka = ra, rkb = rb;                // ranks relative to the candidate set
+      bool synced_after_atomics = false;   // a group barrier has passed since the arg/flag atomics above
+      if (want_median) {
+        uint32_t klo, width, rka, rkb;
+        bool hist_ready;
+        if (use_win) { klo = winL; width = winW; rka = ra - cb; rkb = rb - cb; hist_ready = true; }
+        else { klo = kmn; width = kmx - kmn; rka = ra; rkb = rb; hist_ready = false; }
+        bool win_failed = false;
+        const bool all_equal = (kmx == kmn);
 #pragma unroll 1
-        for (;;) {
-          const int sh = max(0, (32 - __clz(width)) - (C::NBUCKET == 1024 ? 10 : (C::NBUCKET == 512 ? 9 : 8)));
-          // histogram of the candidates
+        while (!all_equal || hist_ready) {   // all-equal frames only need the fused histogram cleared
+          const int sh = max(0, (32 - __clz(width | 1u)) - HBITS);
+          if (!hist_ready) {
 #pragma unroll
-          for (int i = 0; i < E; i++) {
-            const uint32_t t = v2_key<MODE>(val[i]) - klo;
-            if (SA_VALID(i) && t <= width) atomicAdd(&hist[t >> sh], 1u);
-          }
-          if (valid_mid) {
-            const uint32_t t = v2_key<MODE>(vmid) - klo;
-            if (t <= width) atomicAdd(&hist[t >> sh], 1u);
-          }
-          group_sync<T>(g);
-          // scan: BPT buckets per thread, warp inclusive scan, warp totals
-          uint32_t hb[C::BPT];
-          uint32_t local = 0;
-#pragma unroll
-          for (int b = 0; b < C::BPT; b++) { hb[b] = hist[j * C::BPT + b]; local += hb[b]; }
-#pragma unroll
-          for (int b = 0; b < C::BPT; b++) hist[j * C::BPT + b] = 0;
-          uint32_t incl = local;
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += o;
-          }
-          if constexpr (NW > 1) {
-            if (lane == 31) misc[MI_WTOT + wig] = incl;
+            for (int i = 0; i < E; i++) {
+              const uint32_t t = v2_key<MODE>(val[i]) - klo;
+              smem_inc_if(SA_VALID(i) && t <= width, hist_s + ((t >> sh) << 2));
+            }
+            if (valid_mid) {
+              const uint32_t t = v2_key<MODE>(vmid) - klo;
+              smem_inc_if(t <= width, hist_s + ((t >> sh) << 2));
+            }
             group_sync<T>(g);
-#pragma unroll
-            for (int w = 0; w < NW; w++) if (w < wig) incl += misc[MI_WTOT + w];
           }
-          const uint32_t excl = incl - local;
-          if (excl <= rka && rka < incl) {
-            uint32_t c = excl;
+          hist_ready = false;
+          // warp 0 of the group scans the NB buckets (8 per lane), finds the buckets of the two middle
+          // ranks and clears the histogram for its next use
+          if (wig == 0) {
+            uint32_t hb[HBPL];
+            uint32_t local = 0;
 #pragma unroll
-            for (int b = 0; b < C::BPT; b++) {
-              if (rka >= c && rka < c + hb[b]) { misc[MI_SELA] = j * C::BPT + b; misc[MI_SELA + 1] = c; misc[MI_SELA + 2] = hb[b]; }
-              c += hb[b];
+            for (int b = 0; b < HBPL; b++) { hb[b] = hist[lane * HBPL + b]; local += hb[b]; }
+#pragma unroll
+            for (int b = 0; b < HBPL; b++) hist[lane * HBPL + b] = 0;
+            uint32_t incl = local;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+              if (lane >= off) incl += o;
             }
-          }
-          if (excl <= rkb && rkb < incl) {
+            const uint32_t excl = incl - local;
+            if (lane == 0) { misc[MI_SELA] = 0xffffffffu; misc[MI_SELB] = 0xffffffffu; }
+            __syncwarp();
             uint32_t c = excl;
 #pragma unroll
-            for (int b = 0; b < C::BPT; b++) {
-              if (rkb >= c && rkb < c + hb[b]) { misc[MI_SELB] = j * C::BPT + b; misc[MI_SELB + 1] = c; misc[MI_SELB + 2] = hb[b]; }
+            for (int b = 0; b < HBPL; b++) {
+              if (rka >= c && rka < c + hb[b]) { misc[MI_SELA] = lane * HBPL + b; misc[MI_SELA + 1] = c; misc[MI_SELA + 2] = hb[b]; }
+              if (rkb >= c && rkb < c + hb[b]) { misc[MI_SELB] = lane * HBPL + b; }
               c += hb[b];
             }
           }
           group_sync<T>(g);
+          synced_after_atomics = true;
+          if (all_equal) break;
           const uint32_t ba = misc[MI_SELA], below_a = misc[MI_SELA + 1], cnt_a = misc[MI_SELA + 2];
           const uint32_t bb = misc[MI_SELB];
+          if (ba == 0xffffffffu || bb == 0xffffffffu) {
+            // the guessed window does not contain both middle ranks: exact full-range pass instead
+            win_failed = true;
+            klo = kmn; width = kmx - kmn; rka = ra; rkb = rb;
+            continue;
+          }
           if (sh == 0) {  // buckets are single keys
             ka = klo + ba;
             kb = klo + bb;
@@ -516,15 +568,15 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
             break;
           }
           if (cnt_a <= 32) {
-            // compaction of the selected bucket + warp-level rank count
+            // compaction of the selected bucket (predicated, branch-free) + warp-level rank count
 #pragma unroll
             for (int i = 0; i < E; i++) {
               const uint32_t k = v2_key<MODE>(val[i]);
-              if (SA_VALID(i) && (k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u)] = k;
+              smem_push_if(SA_VALID(i) && (k - lo_a) <= bw, k, lcount_s, list_s);
             }
             if (valid_mid) {
               const uint32_t k = v2_key<MODE>(vmid);
-              if ((k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u)] = k;
+              smem_push_if((k - lo_a) <= bw, k, lcount_s, list_s);
             }
             group_sync<T>(g);
             if (wig == 0) {
@@ -539,9 +591,11 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
               const uint32_t mb = __ballot_sync(0xffffffffu, lane < cnt_a && rank == wb);
               ka = __shfl_sync(0xffffffffu, mine, __ffs(ma) - 1);
               kb = __shfl_sync(0xffffffffu, mine, __ffs(mb) - 1);
-              if (lane == 0) misc[MI_LCOUNT] = 0u;
+              if (lane == 0) { misc[MI_LCOUNT] = 0u; misc[MI_GUESS] = kb; }
             }
-            break;  // only warp 0 (thread 0 writes the record) holds ka/kb; others do not need them
+            // only warp 0 (thread 0 writes the record) holds ka/kb
+            gw_next_known = true;
+            break;
           }
           // crowded bucket (many near-equal values): narrow the candidate set and repeat
           klo = lo_a;
@@ -549,9 +603,15 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
           rka -= below_a;
           rkb -= below_a;
         }
+        // adapt the window for the next frame (all values here are group-uniform)
+        if (gw == 0u) gw = GW_INIT;
+        else if (win_failed) gw = (gw < (1u << 28)) ? gw << 2 : gw;
+        else gw = max(gw - (gw >> 6), GW_MIN);
+        if (!gw_next_known && j == 0) misc[MI_GUESS] = kb;   // paths where every thread knows kb
+        gw_next_known = false;
       }
 
-      if (!median_barriers) group_sync<T>(g);  // arg bins / flags complete
+      if (!synced_after_atomics) group_sync<T>(g);  // arg bins / flags complete
       if (j == 0) {
         const bool mm = p.stats_mask & SA_STATS_MINMAX;
         uint4 r0, r1;
