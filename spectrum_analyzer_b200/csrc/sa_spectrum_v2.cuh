@@ -63,7 +63,7 @@ struct V2Cfg {
   static constexpr size_t OFF_TWR = OFF_TW3 + sizeof(float2) * NTW3;
   static constexpr size_t OFF_GROUPS = OFF_TWR + sizeof(float2) * NTWR;
   static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
-  static constexpr size_t G_HIST = sizeof(uint32_t) * (NBUCKET + 8);
+  static constexpr size_t G_HIST = sizeof(uint32_t) * (NBUCKET + 8);   // [below | NBUCKET buckets | above | pad]
   static constexpr size_t G_MISC = sizeof(uint32_t) * 64;
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
   static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST;
@@ -75,15 +75,20 @@ enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_CB = 24, MI_ARGMIN = 32, MI_ARG
        MI_GUESS = 35, MI_SELA = 36 /*b, below, cnt*/, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45, MI_FLAGS = 46,
        MI_UMAX = 48 };
 
-// predicated, branch-free shared-memory helpers (32-bit shared-window addresses)
-__device__ __forceinline__ void smem_inc_if(bool pred, uint32_t saddr) {
-  asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.add.u32 [%1], 1; }" ::"r"((uint32_t)pred), "r"(saddr) : "memory");
-}
-__device__ __forceinline__ void smem_push_if(bool pred, uint32_t key, uint32_t count_saddr, uint32_t list_saddr) {
-  asm volatile(
-      "{ .reg .pred p; .reg .u32 pos; setp.ne.u32 p, %0, 0; @p atom.shared.add.u32 pos, [%1], 1; "
-      "@p and.b32 pos, pos, 31; @p shl.b32 pos, pos, 2; @p add.u32 pos, pos, %2; @p st.shared.u32 [pos], %3; }" ::"r"((uint32_t)pred),
-      "r"(count_saddr), "r"(list_saddr), "r"(key) : "memory");
+// Histogram slot of key k for the candidate window [klo, klo + width] with bucket shift sh:
+// slot 0 = below the window, slots 1..NB = buckets, slot NB+1 = above.  The atomic increment is
+// unconditional (ptxas turns a predicated ATOMS into a branch), the slot index is clamped instead.
+template <int MODE, int NB>
+__device__ __forceinline__ uint32_t hist_slot(uint32_t k, uint32_t klo, int sh) {
+  if constexpr (MODE == SCALE_LOG10) {
+    // ordered keys use all 32 bits: explicit compare for "below"
+    const uint32_t d = min((k - klo) >> sh, (uint32_t)NB) + 1u;
+    return k < klo ? 0u : d;
+  } else {
+    // keys are bit patterns of non-negative floats (< 2^31): the signed difference cannot overflow
+    const int d = (int)(k - klo) >> sh;      // arithmetic shift: negative when k < klo
+    return (uint32_t)(max(min(d, NB), -1) + 1);
+  }
 }
 
 template <int T>
@@ -139,9 +144,6 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   uint32_t *hist = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
   uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
   uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
-  const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-  const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(list);
-  const uint32_t lcount_s = (uint32_t)__cvta_generic_to_shared(misc + MI_LCOUNT);
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
   constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
   uint32_t gw = 0u;                // 0: no guess yet (first frame of the group)
@@ -244,22 +246,21 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
     // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
     {
-      float2 *w = wbuf + (j + (j >> 4));
+      // both sides of this exchange are unit-stride across lanes: no padding needed
+      float2 *w = wbuf + j;
 #pragma unroll
-      for (int s = E / 2; s < E; s++) w[(s - E / 2) * PADT] = x[s];
+      for (int s = E / 2; s < E; s++) w[(s - E / 2) * T] = x[s];
     }
     group_sync<T>(g);
     float val[E];        // val[2s] = bin j + s*T, val[2s+1] = bin M - (j + s*T); (j,s)=(0,0): bins 0 and M
     float vmid = 0.f;    // bin M/2, thread 0 only
     {
-      // partner of k = j + s*T sits at index M/2 - k of the upper-half buffer; T % 16 == 0, so the
-      // padded address is pad(M/2 - j) - s*PADT
-      const int base = M / 2 - j;
-      const float2 *r = wbuf + (base + (base >> 4));
+      // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
+      const float2 *r = wbuf + (M / 2 - j);
 #pragma unroll
       for (int s = 0; s < E / 2; s++) {
         const float2 a = x[s];
-        const float2 bq = r[-s * PADT];
+        const float2 bq = r[-s * T];
         const float2 w = s_twr[j + s * T];
         // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
         const float2 cb = make_float2(bq.x, -bq.y);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       const uint32_t winW = 2u * gw;
       const int shw = max(0, (32 - __clz(winW | 1u)) - HBITS);
 
-      uint32_t kmn = 0xffffffffu, kmx = 0u, cb = 0u;
+      uint32_t kmn = 0xffffffffu, kmx = 0u;
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < E; i++) {
@@ -395,38 +396,26 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       }
       if (use_win) {
 #pragma unroll
-        for (int i = 0; i < E; i++) {
-          const uint32_t k = v2_key<MODE>(val[i]);
-          const uint32_t t = k - winL;
-          cb += (SA_VALID(i) && k < winL) ? 1u : 0u;
-          smem_inc_if(SA_VALID(i) && t <= winW, hist_s + ((t >> shw) << 2));
-        }
-        if (valid_mid) {
-          const uint32_t k = v2_key<MODE>(vmid);
-          const uint32_t t = k - winL;
-          cb += (k < winL) ? 1u : 0u;
-          smem_inc_if(t <= winW, hist_s + ((t >> shw) << 2));
-        }
+        for (int i = 0; i < E; i++)
+          if (SA_VALID(i)) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(val[i]), winL, shw)], 1u);
+        if (valid_mid) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(vmid), winL, shw)], 1u);
       }
       const uint32_t my_kmn = kmn, my_kmx = kmx;
       kmn = __reduce_min_sync(0xffffffffu, kmn);
       kmx = __reduce_max_sync(0xffffffffu, kmx);
-      if (use_win) cb = __reduce_add_sync(0xffffffffu, cb);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
       if constexpr (NW > 1) {
         if (lane == 0) {
           misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum);
-          misc[MI_CB + wig] = cb;
         }
         group_sync<T>(g);
-        kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]); cb = misc[MI_CB];
+        kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
 #pragma unroll
         for (int w = 1; w < NW; w++) {
           kmn = min(kmn, misc[MI_KMIN + w]);
           kmx = max(kmx, misc[MI_KMAX + w]);
           sum += __uint_as_float(misc[MI_SUM + w]);
-          cb += misc[MI_CB + w];
         }
       } else {
         __syncwarp();
@@ -479,22 +468,25 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       if (want_median) {
         uint32_t klo, width, rka, rkb;
         bool hist_ready;
-        if (use_win) { klo = winL; width = winW; rka = ra - cb; rkb = rb - cb; hist_ready = true; }
+        // ranks are relative to everything the current histogram counted (the "below" slot included)
+        if (use_win) { klo = winL; width = winW; rka = ra; rkb = rb; hist_ready = true; }
         else { klo = kmn; width = kmx - kmn; rka = ra; rkb = rb; hist_ready = false; }
         bool win_failed = false;
+        uint32_t cand_lo = 0u, cand_w = 0xffffffffu;   // keys still in play: (key - cand_lo) <= cand_w
         const bool all_equal = (kmx == kmn);
 #pragma unroll 1
         while (!all_equal || hist_ready) {   // all-equal frames only need the fused histogram cleared
           const int sh = max(0, (32 - __clz(width | 1u)) - HBITS);
           if (!hist_ready) {
+            // narrowed passes only count keys that were inside the previous bucket: cand_lo/cand_w
 #pragma unroll
             for (int i = 0; i < E; i++) {
-              const uint32_t t = v2_key<MODE>(val[i]) - klo;
-              smem_inc_if(SA_VALID(i) && t <= width, hist_s + ((t >> sh) << 2));
+              const uint32_t k = v2_key<MODE>(val[i]);
+              if (SA_VALID(i) && (k - cand_lo) <= cand_w) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(k, klo, sh)], 1u);
             }
             if (valid_mid) {
-              const uint32_t t = v2_key<MODE>(vmid) - klo;
-              smem_inc_if(t <= width, hist_s + ((t >> sh) << 2));
+              const uint32_t k = v2_key<MODE>(vmid);
+              if ((k - cand_lo) <= cand_w) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(k, klo, sh)], 1u);
             }
             group_sync<T>(g);
           }
@@ -505,19 +497,20 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
             uint32_t hb[HBPL];
             uint32_t local = 0;
 #pragma unroll
-            for (int b = 0; b < HBPL; b++) { hb[b] = hist[lane * HBPL + b]; local += hb[b]; }
+            for (int b = 0; b < HBPL; b++) { hb[b] = hist[1 + lane * HBPL + b]; local += hb[b]; }
+            const uint32_t nbelow = hist[0];
 #pragma unroll
-            for (int b = 0; b < HBPL; b++) hist[lane * HBPL + b] = 0;
+            for (int b = 0; b < HBPL; b++) hist[1 + lane * HBPL + b] = 0;
+            __syncwarp();
+            if (lane == 0) { hist[0] = 0; hist[C::NBUCKET + 1] = 0; misc[MI_SELA] = 0xffffffffu; misc[MI_SELB] = 0xffffffffu; }
             uint32_t incl = local;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
               const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
               if (lane >= off) incl += o;
             }
-            const uint32_t excl = incl - local;
-            if (lane == 0) { misc[MI_SELA] = 0xffffffffu; misc[MI_SELB] = 0xffffffffu; }
             __syncwarp();
-            uint32_t c = excl;
+            uint32_t c = nbelow + incl - local;   // keys counted before this lane's first bucket
 #pragma unroll
             for (int b = 0; b < HBPL; b++) {
               if (rka >= c && rka < c + hb[b]) { misc[MI_SELA] = lane * HBPL + b; misc[MI_SELA + 1] = c; misc[MI_SELA + 2] = hb[b]; }
@@ -534,6 +527,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
             // the guessed window does not contain both middle ranks: exact full-range pass instead
             win_failed = true;
             klo = kmn; width = kmx - kmn; rka = ra; rkb = rb;
+            cand_lo = 0u; cand_w = 0xffffffffu;
             continue;
           }
           if (sh == 0) {  // buckets are single keys
@@ -568,15 +562,24 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
             break;
           }
           if (cnt_a <= 32) {
-            // compaction of the selected bucket (predicated, branch-free) + warp-level rank count
+            // compaction of the selected bucket: a warp vote skips the warps that hold no candidate
+            uint32_t tmin = 0xffffffffu;
 #pragma unroll
-            for (int i = 0; i < E; i++) {
-              const uint32_t k = v2_key<MODE>(val[i]);
-              smem_push_if(SA_VALID(i) && (k - lo_a) <= bw, k, lcount_s, list_s);
-            }
-            if (valid_mid) {
-              const uint32_t k = v2_key<MODE>(vmid);
-              smem_push_if((k - lo_a) <= bw, k, lcount_s, list_s);
+            for (int i = 0; i < E; i++)
+              if (SA_VALID(i)) tmin = min(tmin, v2_key<MODE>(val[i]) - lo_a);
+            if (valid_mid) tmin = min(tmin, v2_key<MODE>(vmid) - lo_a);
+            if (__any_sync(0xffffffffu, tmin <= bw)) {
+              if (tmin <= bw) {
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                  const uint32_t k = v2_key<MODE>(val[i]);
+                  if (SA_VALID(i) && (k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k;
+                }
+                if (valid_mid) {
+                  const uint32_t k = v2_key<MODE>(vmid);
+                  if ((k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k;
+                }
+              }
             }
             group_sync<T>(g);
             if (wig == 0) {
@@ -600,6 +603,8 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
           // crowded bucket (many near-equal values): narrow the candidate set and repeat
           klo = lo_a;
           width = bw;
+          cand_lo = lo_a;
+          cand_w = bw;
           rka -= below_a;
           rkb -= below_a;
         }
