@@ -63,7 +63,8 @@ struct V2Cfg {
   static constexpr size_t OFF_TWR = OFF_TW3 + sizeof(float2) * NTW3;
   static constexpr size_t OFF_GROUPS = OFF_TWR + sizeof(float2) * NTWR;
   static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
-  static constexpr size_t G_HIST = sizeof(uint32_t) * (NBUCKET + 8);   // [below | NBUCKET buckets | above | pad]
+  static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
+  static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
   static constexpr size_t G_MISC = sizeof(uint32_t) * 64;
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
   static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST;
@@ -71,9 +72,9 @@ struct V2Cfg {
 };
 
 // misc words of a group
-enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_CB = 24, MI_ARGMIN = 32, MI_ARGMAX = 33, MI_LCOUNT = 34,
-       MI_GUESS = 35, MI_SELA = 36 /*b, below, cnt*/, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45, MI_FLAGS = 46,
-       MI_UMAX = 48 };
+enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_ARGMIN = 32, MI_ARGMAX = 33, MI_LCOUNT = 34,
+       MI_GUESS = 35, MI_SELA = 36 /*b, below, cnt*/, MI_LDONE = 39, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45,
+       MI_FLAGS = 46, MI_UMAX = 48 };
 
 // Histogram slot of key k for the candidate window [klo, klo + width] with bucket shift sh:
 // slot 0 = below the window, slots 1..NB = buckets, slot NB+1 = above.  The atomic increment is
@@ -141,13 +142,18 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   unsigned char *gbase = smem + C::OFF_GROUPS + (size_t)g * C::G_BYTES;
   float2 *bufA = reinterpret_cast<float2 *>(gbase);
   float2 *bufB = reinterpret_cast<float2 *>(gbase + C::G_BUF);
-  uint32_t *hist = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
+  uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
   uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
   uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
   constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
   uint32_t gw = 0u;                // 0: no guess yet (first frame of the group)
-  bool gw_next_known = false;
+  int par = 0;                     // which of the two histograms this frame uses
+  // record fields thread 0 writes one barrier later (after every thread finished the frame)
+  bool pend = false, pend_med = false;
+  u64 pend_cur = 0;
+  uint32_t pend_kmn = 0, pend_kmx = 0, pend_medkey = 0;
+  float pend_sum = 0.f;
 
   // ---- one-time: tables -> shared memory, histogram cleared ------------------------------------
   const bool has_win = p.window != nullptr;
@@ -155,7 +161,8 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
   for (int i = tid; i < C::NTW3; i += C::NT) s_tw3[i] = __ldg(P.tw3 + i);
   for (int i = tid; i < C::NTWR; i += C::NT) s_twr[i] = __ldg(P.twr + i);
-  for (int i = j; i < C::NBUCKET + 8; i += T) hist[i] = 0;
+  for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
+  if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
   __syncthreads();
 
   const uint32_t lo = p.bin_lo, hi = p.bin_hi;
@@ -179,9 +186,31 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   }
   float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
 
+  // thread 0: write the record fields of the previous frame (everything except a median written
+  // by the "last pusher"), then reset the per-frame words.  Called right after a group barrier.
+  auto flush_record = [&]() {
+    if (pend) {
+      const bool mm = p.stats_mask & SA_STATS_MINMAX;
+      uint4 r0;
+      r0.x = mm ? __float_as_uint(v2_unkey<MODE>(pend_kmn)) : 0u;
+      r0.y = mm ? misc[MI_ARGMIN] : 0u;
+      r0.z = mm ? __float_as_uint(v2_unkey<MODE>(pend_kmx)) : 0u;
+      r0.w = mm ? misc[MI_ARGMAX] : 0u;
+      uint32_t *rec = reinterpret_cast<uint32_t *>(&p.stats[pend_cur]);
+      *reinterpret_cast<uint4 *>(rec) = r0;
+      rec[4] = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(pend_sum, (float)count)) : 0u;
+      if (pend_med) rec[5] = want_median ? __float_as_uint(v2_unkey<MODE>(pend_medkey)) : 0u;
+      const uint32_t fl = misc[MI_FLAGS];
+      const uint32_t st = (fl & 1u) ? SA_ERR_NAN_VALUES : (fl & 2u) ? SA_ERR_INFINITY_VALUES
+                        : (fl & 4u) ? SA_ERR_NON_FINITE_RESULT : SA_OK;
+      *reinterpret_cast<uint2 *>(rec + 6) = make_uint2(st, 0u);
+      pend = false;
+    }
+    misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u;
+  };
+
 #pragma unroll 1
   for (;;) {
-    if (j == 0) { misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_LCOUNT] = 0u; misc[MI_FLAGS] = 0u; }
 
     // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
 #pragma unroll
@@ -201,6 +230,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       for (int k = 0; k < 16; k++) w[k] = x[k];
     }
     group_sync<T>(g);
+    if (want_stats && j == 0) flush_record();  // every thread of the group has finished the previous frame
     {
       const float2 *r = wbuf + (j + (j >> 4));
 #pragma unroll
@@ -367,10 +397,13 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
     // ---- statistics of the scaled values (src/spectrum.rs:481-539) --------------------------------
     if (want_stats) {
+      uint32_t *hist = hist0 + par * C::HSTRIDE;          // clean on entry
+      uint32_t *hist_other = hist0 + (par ^ 1) * C::HSTRIDE;  // possibly dirty from the previous frame
+      par ^= 1;
       const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;   // middle ranks (0-based)
       // Median window guess: keys within gw of the previous frame's median.  The fused pass below
-      // histograms only those and counts the keys under the window; the selection stays exact
-      // because the ranks are verified against the counts and the full-range pass is the fallback.
+      // histograms all keys against that window (below / 256 buckets / above); the selection stays
+      // exact because the ranks are verified against the counts, with the full-range pass as fallback.
       const bool use_win = want_median && gw != 0u;
       const uint32_t gk = use_win ? misc[MI_GUESS] : 0u;
       const uint32_t winL = gk > gw ? gk - gw : 0u;
@@ -406,9 +439,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
       if constexpr (NW > 1) {
-        if (lane == 0) {
-          misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum);
-        }
+        if (lane == 0) { misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum); }
         group_sync<T>(g);
         kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
 #pragma unroll
@@ -462,18 +493,127 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         atomicOr(&misc[MI_FLAGS], f);
       }
 
-      // ---- median: exact selection -----------------------------------------------------------------
-      uint32_t ka = kmn, kb = kmn;
-      bool synced_after_atomics = false;   // a group barrier has passed since the arg/flag atomics above
-      if (want_median) {
-        uint32_t klo, width, rka, rkb;
-        bool hist_ready;
-        // ranks are relative to everything the current histogram counted (the "below" slot included)
-        if (use_win) { klo = winL; width = winW; rka = ra; rkb = rb; hist_ready = true; }
-        else { klo = kmn; width = kmx - kmn; rka = ra; rkb = rb; hist_ready = false; }
-        bool win_failed = false;
-        uint32_t cand_lo = 0u, cand_w = 0xffffffffu;   // keys still in play: (key - cand_lo) <= cand_w
-        const bool all_equal = (kmx == kmn);
+      const bool all_equal = (kmx == kmn);
+      bool need_slow = false;              // exact selection through the barrier-synchronised loop below
+      bool win_failed = false;
+      uint32_t klo = kmn, width = kmx - kmn, rka = ra, rkb = rb;
+      uint32_t cand_lo = 0u, cand_w = 0xffffffffu;   // keys still in play: (key - cand_lo) <= cand_w
+      bool hist_ready = false;
+
+      if (!want_median || (all_equal && !nonfinite)) {
+        // nothing to select: thread 0 writes the whole record one barrier later
+        if (j == 0) {
+          pend = true; pend_med = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; pend_medkey = kmn;
+          if (want_median) misc[MI_GUESS] = kmn;
+        }
+        if (use_win) {   // the fused pass dirtied this histogram: every warp clears a quarter, used again in 2 frames
+          for (int i = j; i < C::HSTRIDE; i += T) hist_other[i] = 0;
+        }
+        // note: `hist` (dirty when use_win) is cleaned by the next frame's pass over hist_other
+        if (gw == 0u && want_median) gw = GW_INIT;
+      } else if (use_win && (count & 1u) && !nonfinite) {
+        // ---- fast path: no further group barrier -------------------------------------------------
+        // every warp scans the 256 buckets redundantly (8 per lane) and finds the bucket of the middle
+        // rank; the histogram of the previous frame is cleared on the side
+        uint32_t hb[HBPL];
+        uint32_t local = 0;
+#pragma unroll
+        for (int b = 0; b < HBPL; b++) { hb[b] = hist[1 + lane * HBPL + b]; local += hb[b]; }
+        const uint32_t nbelow = hist[0];
+        for (int i = j; i < C::HSTRIDE; i += T) hist_other[i] = 0;
+        uint32_t incl = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += o;
+        }
+        const uint32_t c0 = nbelow + incl - local;
+        const bool own = (ra >= c0) && (ra < c0 + local);
+        const uint32_t om = __ballot_sync(0xffffffffu, own);
+        uint32_t b_sel = 0, below = 0, cnt = 0;
+        if (own) {
+          uint32_t c = c0;
+#pragma unroll
+          for (int b = 0; b < HBPL; b++) {
+            if (ra >= c && ra < c + hb[b]) { b_sel = lane * HBPL + b; below = c; cnt = hb[b]; }
+            c += hb[b];
+          }
+        }
+        const int owner = __ffs(om) - 1;
+        const uint32_t ba = __shfl_sync(0xffffffffu, b_sel, owner & 31);
+        const uint32_t below_a = __shfl_sync(0xffffffffu, below, owner & 31);
+        const uint32_t cnt_a = __shfl_sync(0xffffffffu, cnt, owner & 31);
+        const uint32_t lo_a = winL + (ba << shw), bw = (1u << shw) - 1u;
+        if (om != 0u && cnt_a <= 32u) {
+          if (shw == 0) {
+            // buckets are single keys: the median is lo_a itself; thread 0 writes it with the record
+            if (j == 0) { pend_med = true; pend_medkey = lo_a; misc[MI_GUESS] = lo_a; }
+          } else {
+            // candidates of the selected bucket go to the list; the thread that completes the list
+            // ranks it and writes the median (and the next guess) -- nobody waits for it
+            uint32_t tmin = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < E; i++)
+              if (SA_VALID(i)) tmin = min(tmin, v2_key<MODE>(val[i]) - lo_a);
+            if (valid_mid) tmin = min(tmin, v2_key<MODE>(vmid) - lo_a);
+            if (__any_sync(0xffffffffu, tmin <= bw)) {
+              if (tmin <= bw) {
+                uint32_t npush = 0;
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                  const uint32_t k = v2_key<MODE>(val[i]);
+                  if (SA_VALID(i) && (k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
+                }
+                if (valid_mid) {
+                  const uint32_t k = v2_key<MODE>(vmid);
+                  if ((k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
+                }
+                __threadfence_block();
+                const uint32_t done = atomicAdd(&misc[MI_LDONE], npush) + npush;
+                if (done == cnt_a) {
+                  __threadfence_block();
+                  const volatile uint32_t *vl = list;
+                  const uint32_t want = ra - below_a;
+                  uint32_t res = 0;
+                  for (uint32_t a = 0; a < cnt_a; a++) {
+                    const uint32_t kk = vl[a];
+                    uint32_t r = 0;
+                    for (uint32_t b = 0; b < cnt_a; b++) {
+                      const uint32_t ko = vl[b];
+                      r += (ko < kk || (ko == kk && b < a)) ? 1u : 0u;
+                    }
+                    if (r == want) res = kk;
+                  }
+                  reinterpret_cast<uint32_t *>(&p.stats[cur])[5] = __float_as_uint(v2_unkey<MODE>(res));
+                  misc[MI_GUESS] = res;
+                  misc[MI_LCOUNT] = 0u;
+                  misc[MI_LDONE] = 0u;
+                }
+              }
+            }
+            if (j == 0) pend_med = false;
+          }
+          if (j == 0) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; }
+          gw = max(gw - (gw >> 6), GW_MIN);
+        } else {
+          // the guessed window missed the middle rank, or its bucket is crowded: exact loop below
+          group_sync<T>(g);                                   // every warp has finished scanning
+          for (int i = j; i < C::HSTRIDE; i += T) hist[i] = 0;
+          group_sync<T>(g);
+          need_slow = true;
+          if (om == 0u) { win_failed = true; }
+          else { klo = lo_a; width = bw; cand_lo = lo_a; cand_w = bw; rka = ra - below_a; rkb = rka; }
+        }
+      } else {
+        need_slow = true;
+        for (int i = j; i < C::HSTRIDE; i += T) hist_other[i] = 0;   // may be dirty from a fast-path frame
+        if (use_win) { klo = winL; width = winW; hist_ready = true; }
+      }
+
+      // ---- exact selection, barrier-synchronised (first frame, even counts, fallbacks) ---------------
+      if (need_slow) {
+        uint32_t ka = kmn, kb = kmn;
+        bool synced = false;                 // a group barrier has passed since the arg-bin / flag atomics
 #pragma unroll 1
         while (!all_equal || hist_ready) {   // all-equal frames only need the fused histogram cleared
           const int sh = max(0, (32 - __clz(width | 1u)) - HBITS);
@@ -491,7 +631,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
             group_sync<T>(g);
           }
           hist_ready = false;
-          // warp 0 of the group scans the NB buckets (8 per lane), finds the buckets of the two middle
+          // warp 0 of the group scans the buckets (8 per lane), finds the buckets of the two middle
           // ranks and clears the histogram for its next use
           if (wig == 0) {
             uint32_t hb[HBPL];
@@ -519,7 +659,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
             }
           }
           group_sync<T>(g);
-          synced_after_atomics = true;
+          synced = true;
           if (all_equal) break;
           const uint32_t ba = misc[MI_SELA], below_a = misc[MI_SELA + 1], cnt_a = misc[MI_SELA + 2];
           const uint32_t bb = misc[MI_SELB];
@@ -594,11 +734,9 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
               const uint32_t mb = __ballot_sync(0xffffffffu, lane < cnt_a && rank == wb);
               ka = __shfl_sync(0xffffffffu, mine, __ffs(ma) - 1);
               kb = __shfl_sync(0xffffffffu, mine, __ffs(mb) - 1);
-              if (lane == 0) { misc[MI_LCOUNT] = 0u; misc[MI_GUESS] = kb; }
+              if (lane == 0) misc[MI_LCOUNT] = 0u;
             }
-            // only warp 0 (thread 0 writes the record) holds ka/kb
-            gw_next_known = true;
-            break;
+            break;  // only warp 0 (thread 0 writes the record) holds ka/kb
           }
           // crowded bucket (many near-equal values): narrow the candidate set and repeat
           klo = lo_a;
@@ -611,35 +749,35 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         // adapt the window for the next frame (all values here are group-uniform)
         if (gw == 0u) gw = GW_INIT;
         else if (win_failed) gw = (gw < (1u << 28)) ? gw << 2 : gw;
-        else gw = max(gw - (gw >> 6), GW_MIN);
-        if (!gw_next_known && j == 0) misc[MI_GUESS] = kb;   // paths where every thread knows kb
-        gw_next_known = false;
-      }
-
-      if (!synced_after_atomics) group_sync<T>(g);  // arg bins / flags complete
-      if (j == 0) {
-        const bool mm = p.stats_mask & SA_STATS_MINMAX;
-        uint4 r0, r1;
-        r0.x = mm ? __float_as_uint(v2_unkey<MODE>(kmn)) : 0u;
-        r0.y = mm ? misc[MI_ARGMIN] : 0u;
-        r0.z = mm ? __float_as_uint(v2_unkey<MODE>(kmx)) : 0u;
-        r0.w = mm ? misc[MI_ARGMAX] : 0u;
-        r1.x = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(sum, (float)count)) : 0u;
-        float med = 0.f;
-        if (want_median)
-          med = (count & 1u) ? v2_unkey<MODE>(kb)
-                             : __fdiv_rn(__fadd_rn(v2_unkey<MODE>(ka), v2_unkey<MODE>(kb)), 2.0f);
-        r1.y = __float_as_uint(med);
-        const uint32_t fl = misc[MI_FLAGS];
-        r1.z = (fl & 1u) ? SA_ERR_NAN_VALUES : (fl & 2u) ? SA_ERR_INFINITY_VALUES : (fl & 4u) ? SA_ERR_NON_FINITE_RESULT : SA_OK;
-        r1.w = 0u;
-        uint4 *rec = reinterpret_cast<uint4 *>(&p.stats[cur]);
-        rec[0] = r0;
-        rec[1] = r1;
+        if (!synced) group_sync<T>(g);
+        if (j == 0) {
+          // a group barrier has passed since the arg-bin / flag atomics: write the record now
+          misc[MI_GUESS] = kb;
+          const bool mm = p.stats_mask & SA_STATS_MINMAX;
+          uint4 r0, r1;
+          r0.x = mm ? __float_as_uint(v2_unkey<MODE>(kmn)) : 0u;
+          r0.y = mm ? misc[MI_ARGMIN] : 0u;
+          r0.z = mm ? __float_as_uint(v2_unkey<MODE>(kmx)) : 0u;
+          r0.w = mm ? misc[MI_ARGMAX] : 0u;
+          r1.x = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(sum, (float)count)) : 0u;
+          const float med = (count & 1u) ? v2_unkey<MODE>(kb)
+                                         : __fdiv_rn(__fadd_rn(v2_unkey<MODE>(ka), v2_unkey<MODE>(kb)), 2.0f);
+          r1.y = __float_as_uint(med);
+          const uint32_t fl = misc[MI_FLAGS];
+          r1.z = (fl & 1u) ? SA_ERR_NAN_VALUES : (fl & 2u) ? SA_ERR_INFINITY_VALUES : (fl & 4u) ? SA_ERR_NON_FINITE_RESULT : SA_OK;
+          r1.w = 0u;
+          uint4 *rec = reinterpret_cast<uint4 *>(&p.stats[cur]);
+          rec[0] = r0;
+          rec[1] = r1;
+        }
       }
     }
 #undef SA_VALID
     if (!more) break;
+  }
+  if (want_stats) {
+    group_sync<T>(g);                 // every thread of the group has finished its last frame
+    if (j == 0) flush_record();
   }
 }
 
