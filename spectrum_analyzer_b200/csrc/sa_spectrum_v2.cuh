@@ -128,7 +128,11 @@ __device__ __forceinline__ float div_const(float v, float d, float rd) {
 template <class C, int MODE, bool FULL>
 __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, G = C::G, NW = C::NW, R3 = C::R3, NB3 = C::NB3;
-  constexpr int PADT = T + T / 16;  // padded stride of the strided reads
+  constexpr int PADT = T + T / 16;  // padded stride of the strided reads (first exchange only)
+  // N = 4096: thread j runs the two last-pass butterflies j and 256-j (thread 0: 0 and 128), whose
+  // outputs are exactly each other's mirror bins Z[k] <-> Z[M-k]: the real-FFT recombination then
+  // needs no exchange and no barrier.
+  constexpr bool MIRROR = (NB3 == 2);
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_win = reinterpret_cast<float *>(smem + C::OFF_WIN);
   float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);
@@ -246,70 +250,125 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     }
     dft16(x);
     {
-      // logical index (j/16)*256 + (j%16) + 16 k  ->  padded (j/16)*272 + (j%16) + 17 k
-      float2 *w = wbuf + (j >> 4) * 272 + (j & 15);
+      // second exchange: unit-stride runs of 16 on both sides -> no padding needed
+      float2 *w = wbuf + (j >> 4) * 256 + (j & 15);
 #pragma unroll
-      for (int k = 0; k < 16; k++) w[17 * k] = x[k];
+      for (int k = 0; k < 16; k++) w[16 * k] = x[k];
     }
     group_sync<T>(g);
-    {
-      const float2 *r = wbuf + (j + (j >> 4));
-#pragma unroll
-      for (int s = 0; s < 16; s++) x[s] = r[s * PADT];
-    }
-    { float2 *t = wbuf; wbuf = obuf; obuf = t; }
-
-    // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
-#pragma unroll
-    for (int b = 0; b < NB3; b++) {
-      float2 v[R3];
-#pragma unroll
-      for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
-      const int jb = j + b * T;  // < 256
-#pragma unroll
-      for (int k = 1; k < R3; k++) v[k] = cmul(v[k], s_tw3[(k - 1) * 256 + jb]);
-      dft<R3>(v);
-#pragma unroll
-      for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
-    }
-
-    // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
-    // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
-    {
-      // both sides of this exchange are unit-stride across lanes: no padding needed
-      float2 *w = wbuf + j;
-#pragma unroll
-      for (int s = E / 2; s < E; s++) w[(s - E / 2) * T] = x[s];
-    }
-    group_sync<T>(g);
-    float val[E];        // val[2s] = bin j + s*T, val[2s+1] = bin M - (j + s*T); (j,s)=(0,0): bins 0 and M
+    float val[E];        // magnitudes of the 16 bins this thread owns (bin index: binof(i))
     float vmid = 0.f;    // bin M/2, thread 0 only
-    {
-      // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
-      const float2 *r = wbuf + (M / 2 - j);
+    const int jbB = j ? 256 - j : 128;   // MIRROR: second butterfly of this thread
+    if constexpr (MIRROR) {
+      // ---- pass 3 (last): two radix-8 butterflies, jbA = j -> x[0..7], jbB -> x[8..15] ------------
 #pragma unroll
-      for (int s = 0; s < E / 2; s++) {
-        const float2 a = x[s];
-        const float2 bq = r[-s * T];
-        const float2 w = s_twr[j + s * T];
-        // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
-        const float2 cb = make_float2(bq.x, -bq.y);
-        const float2 pp = add2(a, cb), qq = sub2(a, cb);
-        const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
-        const float2 uu = add2(pp, tt), vv = sub2(pp, tt);
-        val[2 * s] = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
-        val[2 * s + 1] = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
+      for (int k = 0; k < 8; k++) { x[k] = wbuf[j + 256 * k]; x[8 + k] = wbuf[jbB + 256 * k]; }
+      { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+      {
+        float2 va[8], vb[8];
+        va[0] = x[0]; vb[0] = x[8];
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+          va[k] = cmul(x[k], s_tw3[(k - 1) * 256 + j]);
+          vb[k] = cmul(x[8 + k], s_tw3[(k - 1) * 256 + jbB]);
+        }
+        dft8(va);     // va[q] = Z[j   + 256 q]
+        dft8(vb);     // vb[q] = Z[jbB + 256 q]
+        // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ----
+        // pair (k, M-k): 2X[k] = P + T, 2conj(X[M-k]) = P - T with P = A + conj(B), Q = A - conj(B), T = -i w_k Q
+        auto pair_mag = [&](float2 a, float2 bq, float2 w, float &m0, float &m1) {
+          const float2 cb = make_float2(bq.x, -bq.y);
+          const float2 pp = add2(a, cb), qq = sub2(a, cb);
+          const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
+          const float2 uu = add2(pp, tt), vv = sub2(pp, tt);
+          m0 = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
+          m1 = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
+        };
+        const bool t0 = (j == 0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          // kA = j + 256 q pairs with M - kA: held in vb[7-q] (thread 0: its own va[8-q])
+          const float2 p1 = t0 ? va[(8 - q) & 7] : vb[7 - q];
+          pair_mag(va[q], p1, s_twr[j + 256 * q], val[4 * q], val[4 * q + 1]);
+          // kB = jbB + 256 q pairs with M - kB: held in va[7-q] (thread 0: its own vb[7-q])
+          const float2 p2 = t0 ? vb[7 - q] : va[7 - q];
+          pair_mag(vb[q], p2, s_twr[jbB + 256 * q], val[4 * q + 2], val[4 * q + 3]);
+        }
+        if (t0) {
+          val[0] = 2.0f * fabsf(va[0].x + va[0].y);                         // X[0]   = Zr + Zi
+          val[1] = 2.0f * fabsf(va[0].x - va[0].y);                         // X[N/2] = Zr - Zi (packed Nyquist)
+          vmid = 2.0f * sqrt_approx(fmaf(va[4].x, va[4].x, va[4].y * va[4].y));  // X[N/4] = conj(Z[M/2])
+        }
       }
-      if (j == 0) {
-        // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
-        const float2 z0 = x[0];
-        const float2 zm = wbuf[0];
-        val[0] = 2.0f * fabsf(z0.x + z0.y);                      // X[0]   = Zr + Zi
-        val[1] = 2.0f * fabsf(z0.x - z0.y);                      // X[N/2] = Zr - Zi (packed Nyquist)
-        vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
+    } else {
+      {
+        const float2 *r = wbuf + j;
+#pragma unroll
+        for (int s = 0; s < 16; s++) x[s] = r[s * T];
       }
+      { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+
+      // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
+#pragma unroll
+      for (int b = 0; b < NB3; b++) {
+        float2 v[R3];
+#pragma unroll
+        for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
+        const int jb = j + b * T;  // < 256
+#pragma unroll
+        for (int k = 1; k < R3; k++) v[k] = cmul(v[k], s_tw3[(k - 1) * 256 + jb]);
+        dft<R3>(v);
+#pragma unroll
+        for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
+      }
+
+      // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
+      // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
+      {
+        // both sides of this exchange are unit-stride across lanes: no padding needed
+        float2 *w = wbuf + j;
+#pragma unroll
+        for (int s = E / 2; s < E; s++) w[(s - E / 2) * T] = x[s];
+      }
+      group_sync<T>(g);
+      {
+        // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
+        const float2 *r = wbuf + (M / 2 - j);
+#pragma unroll
+        for (int s = 0; s < E / 2; s++) {
+          const float2 a = x[s];
+          const float2 bq = r[-s * T];
+          const float2 w = s_twr[j + s * T];
+          // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
+          const float2 cb = make_float2(bq.x, -bq.y);
+          const float2 pp = add2(a, cb), qq = sub2(a, cb);
+          const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
+          const float2 uu = add2(pp, tt), vv = sub2(pp, tt);
+          val[2 * s] = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
+          val[2 * s + 1] = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
+        }
+        if (j == 0) {
+          // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
+          const float2 z0 = x[0];
+          const float2 zm = wbuf[0];
+          val[0] = 2.0f * fabsf(z0.x + z0.y);                      // X[0]   = Zr + Zi
+          val[1] = 2.0f * fabsf(z0.x - z0.y);                      // X[N/2] = Zr - Zi (packed Nyquist)
+          vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
+        }
+      }
+      { float2 *t = wbuf; wbuf = obuf; obuf = t; }
     }
-    { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+    // bin index of val[i]
+    auto binof = [&](int i) -> uint32_t {
+      if constexpr (MIRROR) {
+        const int q = i >> 2, r = i & 3;
+        const uint32_t k = (uint32_t)(((r & 2) ? jbB : j) + 256 * q);
+        return (r & 1) ? (uint32_t)M - k : k;
+      } else {
+        const uint32_t k = (uint32_t)(j + (i >> 1) * T);
+        return (i & 1) ? (uint32_t)M - k : k;
+      }
+    };
 
     // ---- request the next frame now; its latency hides behind the statistics phase ---------------
     const u64 cur = frame;
@@ -327,11 +386,9 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     if constexpr (!FULL) {
       valid = 0;
 #pragma unroll
-      for (int s = 0; s < E / 2; s++) {
-        const uint32_t k0 = (j == 0 && s == 0) ? 0u : (uint32_t)(j + s * T);
-        const uint32_t k1 = (uint32_t)M - (uint32_t)(j + s * T);
-        valid |= (k0 >= lo && k0 <= hi) ? (1u << (2 * s)) : 0u;
-        valid |= (k1 >= lo && k1 <= hi) ? (2u << (2 * s)) : 0u;
+      for (int i = 0; i < E; i++) {
+        const uint32_t b = binof(i);
+        valid |= (b >= lo && b <= hi) ? (1u << i) : 0u;
       }
       valid_mid = valid_mid && ((uint32_t)(M / 2) >= lo && (uint32_t)(M / 2) <= hi);
     }
@@ -382,16 +439,8 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     {
       float *dst = p.out_vals + cur * p.out_stride - lo;
 #pragma unroll
-      for (int s = 0; s < E / 2; s++) {
-        const int k = j + s * T;
-        if (j == 0 && s == 0) {
-          if (SA_VALID(0)) dst[0] = val[0];
-          if (SA_VALID(1)) dst[M] = val[1];
-        } else {
-          if (SA_VALID(2 * s)) dst[k] = val[2 * s];
-          if (SA_VALID(2 * s + 1)) dst[M - k] = val[2 * s + 1];
-        }
-      }
+      for (int i = 0; i < E; i++)
+        if (SA_VALID(i)) dst[binof(i)] = val[i];
       if (valid_mid) dst[M / 2] = vmid;
     }
 
@@ -455,24 +504,16 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       if (my_kmn == kmn) {
         uint32_t best = 0xffffffffu;
 #pragma unroll
-        for (int s = 0; s < E / 2; s++) {
-          const uint32_t k0 = (j == 0 && s == 0) ? 0u : (uint32_t)(j + s * T);
-          const uint32_t k1 = (uint32_t)M - (uint32_t)(j + s * T);
-          if (SA_VALID(2 * s) && v2_key<MODE>(val[2 * s]) == kmn) best = min(best, k0);
-          if (SA_VALID(2 * s + 1) && v2_key<MODE>(val[2 * s + 1]) == kmn) best = min(best, k1);
-        }
+        for (int i = 0; i < E; i++)
+          if (SA_VALID(i) && v2_key<MODE>(val[i]) == kmn) best = min(best, binof(i));
         if (valid_mid && v2_key<MODE>(vmid) == kmn) best = min(best, (uint32_t)(M / 2));
         atomicMin(&misc[MI_ARGMIN], best);
       }
       if (my_kmx == kmx) {
         uint32_t best = 0u;
 #pragma unroll
-        for (int s = 0; s < E / 2; s++) {
-          const uint32_t k0 = (j == 0 && s == 0) ? 0u : (uint32_t)(j + s * T);
-          const uint32_t k1 = (uint32_t)M - (uint32_t)(j + s * T);
-          if (SA_VALID(2 * s) && v2_key<MODE>(val[2 * s]) == kmx) best = max(best, k0);
-          if (SA_VALID(2 * s + 1) && v2_key<MODE>(val[2 * s + 1]) == kmx) best = max(best, k1);
-        }
+        for (int i = 0; i < E; i++)
+          if (SA_VALID(i) && v2_key<MODE>(val[i]) == kmx) best = max(best, binof(i));
         if (valid_mid && v2_key<MODE>(vmid) == kmx) best = max(best, (uint32_t)(M / 2));
         atomicMax(&misc[MI_ARGMAX], best);
       }
