@@ -221,16 +221,18 @@ def run_ours(args):
 
     # sanity on the results of the timed region (all frames OK, stats ordered)
     st = stats.view(torch.int32).view(frames, 8)
-    assert int((st[:, 6] != 0).sum().item()) == 0, "non-OK frame status"
+    if stats_mask:
+        assert int((st[:, 6] != 0).sum().item()) == 0, "non-OK frame status"
     stf = stats.view(torch.float32).view(frames, 8)
-    assert bool(((stf[:, 0] <= stf[:, 5]) & (stf[:, 5] <= stf[:, 2])).all().item()), "min <= median <= max violated"
+    if stats_mask == 7:
+        assert bool(((stf[:, 0] <= stf[:, 5]) & (stf[:, 5] <= stf[:, 2])).all().item()), "min <= median <= max violated"
 
     # ---- roofline of the dominant (only) kernel: one launch per step -------------------------------
     peak, peak_src = measured_hbm_peak()
     kernel_ms = ms_local / max(launches, 1)
     achieved = ALGO_BYTES_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "sa::spectrum_kernel<SpectrumCfg<12,...>>",
+                "traffic": None, "peak_source": peak_src, "kernel": "sa::spectrum_kernel_v2<V2Cfg<12,4>,SCALE_MUL,FULL> (one launch per step)",
                 "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME, "kernel_ms": kernel_ms,
                 "fp32_tflops_algorithmic": ALGO_FLOPS_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e12}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
