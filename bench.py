@@ -95,6 +95,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_run(frames: int, threads: int, native: bool = True):
     """Times the oracle port (restatement of the reference's CPU path: per-frame hann_window +
     samples_fft_to_spectrum + divide_by_N_sqrt, frames split statically over `threads`)."""
@@ -116,7 +124,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     O.lib(native=True)
     dt, _ = cpu_baseline_run(512 * max(1, threads // 8), threads)               # calibration (untimed)
     rate = 512 * max(1, threads // 8) / dt
@@ -288,7 +296,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle as O
-        threads = O.max_threads()
+        threads = host_threads()
         O.lib(native=True)
         d0, _ = cpu_baseline_run(256 * max(1, threads // 8), threads)
         rate = 256 * max(1, threads // 8) / d0
