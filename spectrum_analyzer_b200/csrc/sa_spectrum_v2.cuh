@@ -438,9 +438,21 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     // ---- store the surviving bins ------------------------------------------------------------------
     {
       float *dst = p.out_vals + cur * p.out_stride - lo;
+      if constexpr (MIRROR) {
+        // four address registers, compile-time offsets of +-256 q
+        float *d0 = dst + j, *d1 = dst + (M - j), *d2 = dst + jbB, *d3 = dst + (M - jbB);
 #pragma unroll
-      for (int i = 0; i < E; i++)
-        if (SA_VALID(i)) dst[binof(i)] = val[i];
+        for (int q = 0; q < 4; q++) {
+          if (SA_VALID(4 * q)) d0[256 * q] = val[4 * q];
+          if (SA_VALID(4 * q + 1)) d1[-256 * q] = val[4 * q + 1];
+          if (SA_VALID(4 * q + 2)) d2[256 * q] = val[4 * q + 2];
+          if (SA_VALID(4 * q + 3)) d3[-256 * q] = val[4 * q + 3];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < E; i++)
+          if (SA_VALID(i)) dst[binof(i)] = val[i];
+      }
       if (valid_mid) dst[M / 2] = vmid;
     }
 
@@ -461,13 +473,27 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
       uint32_t kmn = 0xffffffffu, kmx = 0u;
       float sum = 0.f;
+      if constexpr (FULL) {
+        // all 16 owned bins are kept: pairwise (packed) sums and 3-input min/max
+        float2 acc = make_float2(val[0], val[1]);
 #pragma unroll
-      for (int i = 0; i < E; i++) {
-        if (SA_VALID(i)) {
-          const uint32_t k = v2_key<MODE>(val[i]);
-          kmn = min(kmn, k);
-          kmx = max(kmx, k);
-          sum += val[i];
+        for (int i = 2; i < E; i += 2) acc = add2(acc, make_float2(val[i], val[i + 1]));
+        sum = acc.x + acc.y;
+#pragma unroll
+        for (int i = 0; i < E; i += 2) {
+          const uint32_t k0 = v2_key<MODE>(val[i]), k1 = v2_key<MODE>(val[i + 1]);
+          kmn = min(kmn, min(k0, k1));
+          kmx = max(kmx, max(k0, k1));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+          if (SA_VALID(i)) {
+            const uint32_t k = v2_key<MODE>(val[i]);
+            kmn = min(kmn, k);
+            kmx = max(kmx, k);
+            sum += val[i];
+          }
         }
       }
       if (valid_mid) {
