@@ -20,6 +20,7 @@
 #include "sa_host_math.h"
 #include "sa_spectrum_kernel.cuh"
 #include "sa_spectrum_v2.cuh"
+#include "sa_spectrum_small.cuh"
 
 namespace {
 
@@ -60,6 +61,8 @@ struct sa_ctx {
   KernelPlan plans[16];                                     // per log2n (generic family)
   KernelPlan plans_v2[16][4][2];                            // tuned family: [log2n][scale mode][full range]
   std::map<uint32_t, float2 *> v2_tables;                   // n -> tw2 | tw3 | twr (one allocation)
+  KernelPlan plans_small[16][4][2];                         // small-N family
+  std::map<uint32_t, float2 *> small_tables;                // n -> tw2 | twr
   // host-buffer pipeline
   cudaStream_t h2d = nullptr, d2h = nullptr;
   static constexpr int kSlots = 3;
@@ -204,6 +207,80 @@ int launch_v2(sa_ctx *ctx, const SpectrumParams &p) {
 #undef SA_V2_CASE
 }
 
+// ---- small-N family (N = 64..512) -------------------------------------------------------------------
+template <class C>
+int get_small_tables(sa_ctx *ctx, V2Params &P) {
+  auto it = ctx->small_tables.find(C::N);
+  if (it == ctx->small_tables.end()) {
+    const std::vector<float> w = sa_host::twiddle_table(C::N);
+    std::vector<float> host(2 * (size_t)(C::NTW2 + C::NTWR));
+    size_t o = 0;
+    auto put = [&](size_t idx) { host[o++] = w[2 * idx]; host[o++] = w[2 * idx + 1]; };
+    for (int k = 1; k < C::R2; k++)                    // pass 2: w_M^(k p) = W_N[2 k p]
+      for (int pp = 0; pp < 16; pp++) put((size_t)2 * k * pp);
+    for (int k = 0; k < C::NTWR; k++) put((size_t)k);  // recombination: W_N^k
+    float2 *dev = nullptr;
+    SA_CUDA(cudaMalloc(&dev, host.size() * sizeof(float)));
+    SA_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->small_tables.emplace(C::N, dev).first;
+  }
+  P.tw2 = it->second;
+  P.tw3 = nullptr;
+  P.twr = P.tw2 + C::NTW2;
+  return SA_OK;
+}
+
+template <class C, int MODE, bool FULL>
+int launch_small_inst(sa_ctx *ctx, const V2Params &P) {
+  KernelPlan &plan = ctx->plans_small[C::LOG2N][MODE][FULL ? 1 : 0];
+  auto kernel = spectrum_kernel_small<C, MODE, FULL>;
+  if (!plan.ready) {
+    SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TOTAL));
+    int per_sm = 0;
+    SA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::NT, C::SMEM_TOTAL));
+    if (per_sm < 1) { g_last_error = "small kernel does not fit on an SM"; return SA_ERR_CUDA; }
+    plan.max_blocks = per_sm * ctx->num_sms;
+    plan.ready = true;
+  }
+  const u64 per_cta = (u64)C::WARPS * C::FPW;
+  const u64 needed = (P.b.n_frames + per_cta - 1) / per_cta;
+  const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
+  kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(P);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+template <class C>
+int launch_small(sa_ctx *ctx, const SpectrumParams &p) {
+  V2Params P;
+  P.b = p;
+  int e = get_small_tables<C>(ctx, P);
+  if (e != SA_OK) return e;
+  const bool full = p.bin_lo == 0 && p.bin_hi == (uint32_t)C::M;
+  int mode = SCALE_MUL;
+  P.cmul = 0.5f;
+  P.div = 1.0f;
+  P.rdiv = 1.0f;
+  switch (p.scaling_kind) {
+    case SA_SCALING_NONE: break;
+    case SA_SCALING_DIVIDE_BY_N: P.cmul = 0.5f / (float)C::N; break;
+    case SA_SCALING_DIVIDE_BY_N_SQRT:
+      if (C::LOG2N % 2 == 0) P.cmul = 0.5f / p.scale_div;
+      else { mode = SCALE_DIV; P.div = p.scale_div; P.rdiv = 1.0f / p.scale_div; }
+      break;
+    case SA_SCALING_ZERO_TO_ONE: mode = SCALE_ZERO_ONE; break;
+    default: mode = SCALE_LOG10; break;
+  }
+  switch (mode) {
+    case SCALE_MUL: return full ? launch_small_inst<C, SCALE_MUL, true>(ctx, P) : launch_small_inst<C, SCALE_MUL, false>(ctx, P);
+    case SCALE_DIV: return full ? launch_small_inst<C, SCALE_DIV, true>(ctx, P) : launch_small_inst<C, SCALE_DIV, false>(ctx, P);
+    case SCALE_ZERO_ONE: return full ? launch_small_inst<C, SCALE_ZERO_ONE, true>(ctx, P) : launch_small_inst<C, SCALE_ZERO_ONE, false>(ctx, P);
+    default: return full ? launch_small_inst<C, SCALE_LOG10, true>(ctx, P) : launch_small_inst<C, SCALE_LOG10, false>(ctx, P);
+  }
+}
+
 int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
   if (p.n_frames == 0) return SA_OK;
   switch (log2n) {
@@ -214,10 +291,10 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
       SA_CUDA(cudaGetLastError());
       return SA_OK;
     }
-    case 6: return launch_cfg<SpectrumCfg<6, 8, 32>>(ctx, p, log2n);
-    case 7: return launch_cfg<SpectrumCfg<7, 8, 16>>(ctx, p, log2n);
-    case 8: return launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n);
-    case 9: return launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n);
+    case 6: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<6, 8, 32>>(ctx, p, log2n) : launch_small<SmallCfg<6>>(ctx, p);
+    case 7: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<7, 8, 16>>(ctx, p, log2n) : launch_small<SmallCfg<7>>(ctx, p);
+    case 8: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n) : launch_small<SmallCfg<8>>(ctx, p);
+    case 9: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n) : launch_small<SmallCfg<9>>(ctx, p);
     case 10: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, 16>>(ctx, p);
     case 11: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
     case 12: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
@@ -392,6 +469,7 @@ int sa_ctx_destroy(sa_ctx *ctx) {
   for (auto &kv : ctx->twiddles) cudaFree(kv.second);
   for (auto &kv : ctx->windows) cudaFree(kv.second);
   for (auto &kv : ctx->v2_tables) cudaFree(kv.second);
+  for (auto &kv : ctx->small_tables) cudaFree(kv.second);
   for (int s = 0; s < sa_ctx::kSlots; s++) {
     cudaFree(ctx->slot_in[s]); cudaFree(ctx->slot_out[s]); cudaFree(ctx->slot_stats[s]);
     if (ctx->pipeline_ready) { cudaEventDestroy(ctx->ev_h2d[s]); cudaEventDestroy(ctx->ev_comp[s]); cudaEventDestroy(ctx->ev_d2h[s]); }
