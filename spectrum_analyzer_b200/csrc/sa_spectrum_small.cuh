@@ -43,6 +43,8 @@ enum { SM_ARGMIN = 0, SM_ARGMAX = 1, SM_LCOUNT = 2, SM_FLAGS = 3, SM_RESA = 4, S
 template <class C, int MODE, bool FULL>
 __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params P) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, FPW = C::FPW, R2 = C::R2, NB2 = C::NB2;
+  constexpr bool ODD = FULL;                         // FrequencyLimit::All keeps N/2+1 bins: one middle rank
+  constexpr uint32_t LIST_MAX = (2 * T > 8) ? 2 * T : 8;   // larger buckets are narrowed by another pass
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_win = reinterpret_cast<float *>(smem + C::OFF_WIN);
   float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);
@@ -311,24 +313,26 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
 #pragma unroll
             for (int b = 0; b < 8; b++) {
               if (rka >= c && rka < c + hb[b]) { own_a = true; sa_b = j * 8 + b; sa_below = c; sa_cnt = hb[b]; }
-              if (rkb >= c && rkb < c + hb[b]) { own_b = true; sb_b = j * 8 + b; }
+              if (!ODD && rkb >= c && rkb < c + hb[b]) { own_b = true; sb_b = j * 8 + b; }
               c += hb[b];
             }
           }
           const uint32_t bal_a = (__ballot_sync(0xffffffffu, own_a) >> (fl * T)) & (T == 16 ? 0xffffu : ((1u << T) - 1u));
-          const uint32_t bal_b = (__ballot_sync(0xffffffffu, own_b) >> (fl * T)) & (T == 16 ? 0xffffu : ((1u << T) - 1u));
+          uint32_t bal_b = bal_a;
+          if constexpr (!ODD) bal_b = (__ballot_sync(0xffffffffu, own_b) >> (fl * T)) & (T == 16 ? 0xffffu : ((1u << T) - 1u));
           const int oa = bal_a ? __ffs(bal_a) - 1 : 0, ob = bal_b ? __ffs(bal_b) - 1 : 0;
           const uint32_t ba = __shfl_sync(0xffffffffu, sa_b, oa, T);
           const uint32_t below_a = __shfl_sync(0xffffffffu, sa_below, oa, T);
           const uint32_t cnt_a = __shfl_sync(0xffffffffu, sa_cnt, oa, T);
-          const uint32_t bb = __shfl_sync(0xffffffffu, sb_b, ob, T);
+          uint32_t bb = ba;
+          if constexpr (!ODD) bb = __shfl_sync(0xffffffffu, sb_b, ob, T);
           const uint32_t lo_a = klo + (ba << sh), lo_b = klo + (bb << sh), bw = (sh ? (1u << sh) : 1u) - 1u;
           const bool single = !done && sh == 0;
           const bool split = !done && sh != 0 && ba != bb;
-          const bool uselist = !done && sh != 0 && ba == bb && cnt_a <= 32u;
-          const bool refine = !done && sh != 0 && ba == bb && cnt_a > 32u;
+          const bool uselist = !done && sh != 0 && ba == bb && cnt_a <= LIST_MAX;
+          const bool refine = !done && sh != 0 && ba == bb && cnt_a > LIST_MAX;
           if (single) { ka = klo + ba; kb = klo + bb; }
-          if (__any_sync(0xffffffffu, split)) {
+          if (!ODD && __any_sync(0xffffffffu, split)) {
             uint32_t ma = 0u, mb = 0xffffffffu;
 #pragma unroll
             for (int i = 0; i < E; i++) {
