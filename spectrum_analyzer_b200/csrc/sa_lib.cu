@@ -135,14 +135,17 @@ int get_v2_tables(sa_ctx *ctx, V2Params &P) {
   auto it = ctx->v2_tables.find(C::N);
   if (it == ctx->v2_tables.end()) {
     const std::vector<float> w = sa_host::twiddle_table(C::N);  // W_N[i], i < N
-    std::vector<float> host(2 * (size_t)(C::NTW2 + C::NTW3 + C::NTWR));
+    std::vector<float> host(2 * (size_t)(C::NTW2 + C::NTW3 + C::NTWR + C::NTW4));
     size_t o = 0;
     auto put = [&](size_t idx) { host[o++] = w[2 * idx]; host[o++] = w[2 * idx + 1]; };
     for (int k = 1; k < 16; k++)                       // pass 2: w_256^(k p) = W_N[k p N/256]
       for (int pp = 0; pp < 16; pp++) put((size_t)k * pp * (C::N / 256));
-    for (int k = 1; k < C::R3; k++)                    // pass 3: w_M^(k p) = W_N[2 k p]
-      for (int pp = 0; pp < 256; pp++) put((size_t)2 * k * pp);
+    for (int k = 1; k < C::R3; k++)                    // pass 3: w_(256 R3)^(k p) = W_N[k p N/(256 R3)]
+      for (int pp = 0; pp < 256; pp++) put((size_t)k * pp * (C::N / (256 * C::R3)));
     for (int k = 0; k < C::NTWR; k++) put((size_t)k);  // recombination: W_N^k
+    if (C::FOUR)
+      for (int k = 1; k < C::R4; k++)                  // pass 4: w_M^(k p) = W_N[2 k p]
+        for (int pp = 0; pp < 4096; pp++) put((size_t)2 * k * pp);
     float2 *dev = nullptr;
     SA_CUDA(cudaMalloc(&dev, host.size() * sizeof(float)));
     SA_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -152,6 +155,7 @@ int get_v2_tables(sa_ctx *ctx, V2Params &P) {
   P.tw2 = it->second;
   P.tw3 = P.tw2 + C::NTW2;
   P.twr = P.tw3 + C::NTW3;
+  P.tw4 = P.twr + C::NTWR;
   return SA_OK;
 }
 
@@ -299,7 +303,7 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 11: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
     case 12: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
     case 13: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
-    case 14: return launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n);
+    case 14: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<14, 1>>(ctx, p);
     case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
     default: return SA_ERR_UNSUPPORTED_LENGTH;
   }

@@ -39,6 +39,7 @@ struct V2Params {
   const float2 *tw2;   // [15][16]           w_256^(k*p)
   const float2 *tw3;   // [R3-1][256]        w_M^(k*p)
   const float2 *twr;   // [M/2]              W_N^k  (recombination)
+  const float2 *tw4;   // [R4-1][4096]       w_M^(k*p)  (N = 16384 only: fourth pass)
   float cmul;          // SCALE_MUL: 0.5/div (exact power of two); else 0.5
   float div;           // SCALE_DIV: divisor d
   float rdiv;          // SCALE_DIV: RN(1/d)
@@ -48,33 +49,39 @@ template <int LOG2N_, int G_>
 struct V2Cfg {
   static constexpr int LOG2N = LOG2N_, N = 1 << LOG2N_, M = N / 2, E = 16, T = M / E, G = G_, NT = T * G_;
   static constexpr int NW = T / 32;                  // warps per group
-  static constexpr int R3 = M / 256;                 // radix of the last pass (2, 4, 8 or 16)
-  static constexpr int NB3 = 16 / R3;                // butterflies per thread in the last pass
+  static constexpr bool FOUR = (M > 4096);           // N = 16384: passes 16,16,16,R4 instead of 16,16,R3
+  static constexpr int R3 = FOUR ? 16 : M / 256;     // radix of the third pass (last pass unless FOUR)
+  static constexpr int NB3 = 16 / R3;                // butterflies per thread in the third pass
+  static constexpr int R4 = FOUR ? M / 4096 : 2;     // radix of the fourth (last) pass when FOUR
+  static constexpr int NB4 = 16 / R4;
   static constexpr int BUF = M + M / 16;             // padded float2 elements of one exchange buffer
   static constexpr int HBITS = 8, NBUCKET = 1 << HBITS;   // median histogram: 256 buckets per pass
   static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
-  static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2;
-  static_assert(T % 32 == 0 && T >= 32 && T <= 256, "v2 covers N = 1024..8192");
+  // big frames keep the window and the large twiddle tables in global memory (L1/L2, coalesced)
+  static constexpr bool GLOBAL_TABLES = FOUR;
+  static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2, NTW4 = FOUR ? (R4 - 1) * 4096 : 0;
+  static constexpr int S_WIN = GLOBAL_TABLES ? 0 : N, S_TWR = GLOBAL_TABLES ? 0 : NTWR;
+  static_assert(T % 32 == 0 && T >= 32 && T <= 512, "v2 covers N = 1024..16384");
   static_assert(NT <= 1024 && (T == 32 || G_ <= 15), "named barriers 1..15");
   // shared memory map (bytes)
   static constexpr size_t OFF_WIN = 0;
-  static constexpr size_t OFF_TW2 = OFF_WIN + sizeof(float) * N;
+  static constexpr size_t OFF_TW2 = OFF_WIN + sizeof(float) * S_WIN;
   static constexpr size_t OFF_TW3 = OFF_TW2 + sizeof(float2) * NTW2;
   static constexpr size_t OFF_TWR = OFF_TW3 + sizeof(float2) * NTW3;
-  static constexpr size_t OFF_GROUPS = OFF_TWR + sizeof(float2) * NTWR;
+  static constexpr size_t OFF_GROUPS = OFF_TWR + sizeof(float2) * S_TWR;
   static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
   static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
   static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
-  static constexpr size_t G_MISC = sizeof(uint32_t) * 64;
+  static constexpr size_t G_MISC = sizeof(uint32_t) * 96;
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
   static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST;
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
 };
 
 // misc words of a group
-enum { MI_KMIN = 0, MI_KMAX = 8, MI_SUM = 16, MI_ARGMIN = 32, MI_ARGMAX = 33, MI_LCOUNT = 34,
-       MI_GUESS = 35, MI_SELA = 36 /*b, below, cnt*/, MI_LDONE = 39, MI_SELB = 40, MI_RESA = 44, MI_RESB = 45,
-       MI_FLAGS = 46, MI_UMAX = 48 };
+enum { MI_KMIN = 0, MI_KMAX = 16, MI_SUM = 32, MI_ARGMIN = 48, MI_ARGMAX = 49, MI_LCOUNT = 50,
+       MI_GUESS = 51, MI_SELA = 52 /*b, below, cnt*/, MI_LDONE = 55, MI_SELB = 56, MI_RESA = 57, MI_RESB = 58,
+       MI_FLAGS = 59, MI_UMAX = 64 };
 
 // Histogram slot of key k for the candidate window [klo, klo + width] with bucket shift sh:
 // slot 0 = below the window, slots 1..NB = buckets, slot NB+1 = above.  The atomic increment is
@@ -161,10 +168,25 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
   // ---- one-time: tables -> shared memory, histogram cleared ------------------------------------
   const bool has_win = p.window != nullptr;
-  for (int i = tid; i < N; i += C::NT) s_win[i] = has_win ? __ldg(p.window + i) : 1.0f;
+  if constexpr (!C::GLOBAL_TABLES)
+    for (int i = tid; i < N; i += C::NT) s_win[i] = has_win ? __ldg(p.window + i) : 1.0f;
   for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
   for (int i = tid; i < C::NTW3; i += C::NT) s_tw3[i] = __ldg(P.tw3 + i);
-  for (int i = tid; i < C::NTWR; i += C::NT) s_twr[i] = __ldg(P.twr + i);
+  if constexpr (!C::GLOBAL_TABLES)
+    for (int i = tid; i < C::NTWR; i += C::NT) s_twr[i] = __ldg(P.twr + i);
+  // window multiplier pair / recombination twiddle: shared memory, or global memory for big frames
+  auto win2 = [&](int n) -> float2 {   // multipliers of samples 2n, 2n+1
+    if constexpr (C::GLOBAL_TABLES) return has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + n) : make_float2(1.f, 1.f);
+    else return *reinterpret_cast<const float2 *>(s_win + 2 * n);
+  };
+  auto win1 = [&](int n) -> float {
+    if constexpr (C::GLOBAL_TABLES) return has_win ? __ldg(p.window + n) : 1.0f;
+    else return s_win[n];
+  };
+  auto twr_at = [&](int k) -> float2 {
+    if constexpr (C::GLOBAL_TABLES) return __ldg(P.twr + k);
+    else return s_twr[k];
+  };
   for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
   if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
   __syncthreads();
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
 #pragma unroll
     for (int s = 0; s < E; s++) {
-      const float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * (j + s * T));
+      const float2 w = win2(j + s * T);
       // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
       // skip the rounding of the windowed sample that the reference performs (src/windows.rs:47)
       x[s].x = __fmul_rn(w.x, x[s].x);
@@ -289,10 +311,10 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         for (int q = 0; q < 4; q++) {
           // kA = j + 256 q pairs with M - kA: held in vb[7-q] (thread 0: its own va[8-q])
           const float2 p1 = t0 ? va[(8 - q) & 7] : vb[7 - q];
-          pair_mag(va[q], p1, s_twr[j + 256 * q], val[4 * q], val[4 * q + 1]);
+          pair_mag(va[q], p1, twr_at(j + 256 * q), val[4 * q], val[4 * q + 1]);
           // kB = jbB + 256 q pairs with M - kB: held in va[7-q] (thread 0: its own vb[7-q])
           const float2 p2 = t0 ? vb[7 - q] : va[7 - q];
-          pair_mag(vb[q], p2, s_twr[jbB + 256 * q], val[4 * q + 2], val[4 * q + 3]);
+          pair_mag(vb[q], p2, twr_at(jbB + 256 * q), val[4 * q + 2], val[4 * q + 3]);
         }
         if (t0) {
           val[0] = 2.0f * fabsf(va[0].x + va[0].y);                         // X[0]   = Zr + Zi
@@ -308,18 +330,53 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       }
       { float2 *t = wbuf; wbuf = obuf; obuf = t; }
 
-      // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
+      if constexpr (C::FOUR) {
+        // ---- pass 3: radix 16, NS = 256 (one butterfly per thread) ---------------------------------
+        {
+          const int p3 = j & 255;
 #pragma unroll
-      for (int b = 0; b < NB3; b++) {
-        float2 v[R3];
+          for (int k = 1; k < 16; k++) x[k] = cmul(x[k], s_tw3[(k - 1) * 256 + p3]);
+        }
+        dft16(x);
+        {
+          float2 *w = wbuf + (j >> 8) * 4096 + (j & 255);
 #pragma unroll
-        for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
-        const int jb = j + b * T;  // < 256
+          for (int k = 0; k < 16; k++) w[256 * k] = x[k];
+        }
+        group_sync<T>(g);
+        {
+          const float2 *r = wbuf + j;
 #pragma unroll
-        for (int k = 1; k < R3; k++) v[k] = cmul(v[k], s_tw3[(k - 1) * 256 + jb]);
-        dft<R3>(v);
+          for (int s = 0; s < 16; s++) x[s] = r[s * T];
+        }
+        { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+        // ---- pass 4 (last): radix R4, NS = 4096; twiddles w_M^(k p) from global memory ---------------
 #pragma unroll
-        for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
+        for (int b = 0; b < C::NB4; b++) {
+          float2 v[C::R4];
+#pragma unroll
+          for (int k = 0; k < C::R4; k++) v[k] = x[b + k * C::NB4];
+          const int jb = j + b * T;  // < 4096
+#pragma unroll
+          for (int k = 1; k < C::R4; k++) v[k] = cmul(v[k], __ldg(P.tw4 + (k - 1) * 4096 + jb));
+          dft<C::R4>(v);
+#pragma unroll
+          for (int k = 0; k < C::R4; k++) x[b + k * C::NB4] = v[k];
+        }
+      } else {
+        // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
+#pragma unroll
+        for (int b = 0; b < NB3; b++) {
+          float2 v[R3];
+#pragma unroll
+          for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
+          const int jb = j + b * T;  // < 256
+#pragma unroll
+          for (int k = 1; k < R3; k++) v[k] = cmul(v[k], s_tw3[(k - 1) * 256 + jb]);
+          dft<R3>(v);
+#pragma unroll
+          for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
+        }
       }
 
       // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
@@ -338,7 +395,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         for (int s = 0; s < E / 2; s++) {
           const float2 a = x[s];
           const float2 bq = r[-s * T];
-          const float2 w = s_twr[j + s * T];
+          const float2 w = twr_at(j + s * T);
           // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
           const float2 cb = make_float2(bq.x, -bq.y);
           const float2 pp = add2(a, cb), qq = sub2(a, cb);
@@ -553,7 +610,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         const float *src = p.samples + cur * p.frame_stride;
         uint32_t f = 4u;
         for (int n = j; n < N; n += T) {
-          const float v = __fmul_rn(s_win[n], __ldg(src + n));
+          const float v = __fmul_rn(win1(n), __ldg(src + n));
           if (v != v) f |= 1u;
           if (fabsf(v) == INFINITY) f |= 2u;
         }
