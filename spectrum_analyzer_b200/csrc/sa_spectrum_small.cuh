@@ -274,6 +274,16 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
         uint32_t klo = kmn, width = kmx - kmn, rka = ra, rkb = rb;
         uint32_t cand_lo = 0u, cand_w = 0xffffffffu;
         bool done = (kmx == kmn) || !cur_active;
+        // first pass: a window around the mean (mean +- (max-min)/8 in value space) instead of [min,max];
+        // the "below"/"above" slots keep the ranks exact, and a window that misses the middle rank is
+        // detected below (no owner bucket) and replaced by the full range
+        bool windowed = false;
+        if (!done) {
+          const float vmin = v2_unkey<MODE>(kmn), vmax = v2_unkey<MODE>(kmx);
+          const float mean = sum / (float)count, d = (vmax - vmin) * 0.125f;
+          const uint32_t wlo = v2_key<MODE>(fmaxf(mean - d, vmin)), whi = v2_key<MODE>(fminf(mean + d, vmax));
+          if (whi > wlo && wlo >= kmn && whi <= kmx) { klo = wlo; width = whi - wlo; windowed = true; }
+        }
 #pragma unroll 1
         while (__any_sync(0xffffffffu, !done)) {
           const int sh = max(0, (32 - __clz(width | 1u)) - C::LOGNB);
@@ -327,10 +337,13 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
           uint32_t bb = ba;
           if constexpr (!ODD) bb = __shfl_sync(0xffffffffu, sb_b, ob, T);
           const uint32_t lo_a = klo + (ba << sh), lo_b = klo + (bb << sh), bw = (sh ? (1u << sh) : 1u) - 1u;
-          const bool single = !done && sh == 0;
-          const bool split = !done && sh != 0 && ba != bb;
-          const bool uselist = !done && sh != 0 && ba == bb && cnt_a <= LIST_MAX;
-          const bool refine = !done && sh != 0 && ba == bb && cnt_a > LIST_MAX;
+          // the window missed a middle rank (it fell into the below/above slot): redo with the full range
+          const bool miss = !done && windowed && (bal_a == 0u || bal_b == 0u);
+          windowed = false;
+          const bool single = !done && !miss && sh == 0;
+          const bool split = !done && !miss && sh != 0 && ba != bb;
+          const bool uselist = !done && !miss && sh != 0 && ba == bb && cnt_a <= LIST_MAX;
+          const bool refine = !done && !miss && sh != 0 && ba == bb && cnt_a > LIST_MAX;
           if (single) { ka = klo + ba; kb = klo + bb; }
           if (!ODD && __any_sync(0xffffffffu, split)) {
             uint32_t ma = 0u, mb = 0xffffffffu;
@@ -380,7 +393,9 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
             kb = misc[SM_RESB];
             if (j == 0) misc[SM_LCOUNT] = 0u;
           }
-          if (refine) {
+          if (miss) {
+            klo = kmn; width = kmx - kmn;
+          } else if (refine) {
             klo = lo_a; width = bw; cand_lo = lo_a; cand_w = bw;
             rka -= below_a; rkb -= below_a;
           } else {
