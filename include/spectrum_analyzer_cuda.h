@@ -184,6 +184,13 @@ int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint
                              uint64_t stride, uint32_t bin_lo, uint32_t n, int scaling_kind,
                              uint32_t stats_mask, sa_frame_stats *d_stats);
 
+/* `scaling::combined(&[f1, f2, ...])` (src/scaling.rs:174-182) applied through apply_scaling_fn on a
+ * device-resident batch: every function of the chain (at most 8 built-in kinds) sees the SAME
+ * statistics -- those of the spectrum before the call -- then d_stats[f] is recomputed once. */
+int sa_apply_scaling_chain_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint32_t n_bins,
+                                   uint64_t stride, uint32_t bin_lo, uint32_t n, const int *scaling_kinds,
+                                   uint32_t n_kinds, uint32_t stats_mask, sa_frame_stats *d_stats);
+
 /* windows::*_window on a device-resident batch: d_out[f*n + i] = w_i * d_in[f*frame_stride + i]. */
 int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t n_frames, uint32_t n,
                       uint64_t frame_stride, float *d_out);

@@ -123,7 +123,24 @@ class _ScalingFn:
         raise TypeError(f"scaling.{self.name} is a device-side built-in token, not a host callable")
 
 
+@dataclass(frozen=True)
+class _ScalingChain:
+    kinds: tuple
+
+    def __call__(self, *a, **k):
+        raise TypeError("scaling.combined(...) is a device-side token, not a host callable")
+
+
 class scaling:  # namespace, like the crate's `scaling` module
+    @staticmethod
+    def combined(fncs) -> "_ScalingChain":
+        """`scaling::combined(&[f1, f2, ...])` (src/scaling.rs:174-182): every function of the chain sees the
+        same pre-call statistics.  Usable with FrequencySpectrum.apply_scaling_fn."""
+        kinds = tuple(_scaling_kind(f) for f in fncs)
+        if len(kinds) > 8:
+            raise ValueError("at most 8 functions in a combined chain")
+        return _ScalingChain(kinds)
+
     divide_by_N = _ScalingFn(A.SCALING_DIVIDE_BY_N, "divide_by_N")
     divide_by_N_sqrt = _ScalingFn(A.SCALING_DIVIDE_BY_N_SQRT, "divide_by_N_sqrt")
     scale_to_zero_to_one = _ScalingFn(A.SCALING_ZERO_TO_ONE, "scale_to_zero_to_one")
@@ -293,14 +310,16 @@ class FrequencySpectrum:
     # -- FrequencySpectrum::apply_scaling_fn (src/spectrum.rs:128-168), on the device --
     def apply_scaling_fn(self, scaling_fn) -> None:
         import torch
-        kind = _scaling_kind(scaling_fn)
+        kinds = scaling_fn.kinds if isinstance(scaling_fn, _ScalingChain) else (_scaling_kind(scaling_fn),)
         ctx = self._ctx or default_context()
         dev = torch.device("cuda", ctx.device)
         vals = torch.from_numpy(self._vals.copy()).to(dev)
         st = torch.from_numpy(np.frombuffer(np.asarray(self._stats).tobytes(), np.uint8).copy()).to(dev)
         torch.cuda.synchronize(dev)
-        _check(A.load().sa_apply_scaling_batched(ctx._h, vals.data_ptr(), 1, vals.numel(), vals.numel(),
-                                                 self._bin_lo, self._n, kind, A.STATS_ALL, st.data_ptr()))
+        karr = (C.c_int * max(len(kinds), 1))(*kinds)
+        _check(A.load().sa_apply_scaling_chain_batched(ctx._h, vals.data_ptr(), 1, vals.numel(), vals.numel(),
+                                                       self._bin_lo, self._n, karr, len(kinds), A.STATS_ALL,
+                                                       st.data_ptr()))
         ctx.sync()
         self._vals = vals.cpu().numpy()
         self._stats = np.frombuffer(st.cpu().numpy().tobytes(), A.FRAME_STATS_DTYPE)[0]

@@ -177,8 +177,14 @@ __device__ __forceinline__ uint32_t block_select(const float *vals, uint32_t m, 
   return prefix;
 }
 
+struct ScalingChain {
+  int kind[8];
+  float div[8];   // stats.n or sqrtf(stats.n) per step
+  int count;
+};
+
 __global__ void __launch_bounds__(RESCALE_THREADS) rescale_kernel(float *vals, u64 n_frames, uint32_t m, u64 stride,
-                                                                   uint32_t bin_lo, int scaling_kind, float div,
+                                                                   uint32_t bin_lo, const ScalingChain chain,
                                                                    uint32_t stats_mask, sa_frame_stats *stats) {
   __shared__ u64 scratch[RESCALE_THREADS / 32];
   __shared__ uint32_t hist[256];
@@ -191,7 +197,9 @@ __global__ void __launch_bounds__(RESCALE_THREADS) rescale_kernel(float *vals, u
     float sum = 0.f;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < m; i += RESCALE_THREADS) {
-      const float s = apply_scaling(scaling_kind, v[i], div, vmax) + 0.0f;
+      float s = v[i];
+      for (int c = 0; c < chain.count; c++) s = apply_scaling(chain.kind[c], s, chain.div[c], vmax);  // same stats for every step
+      s = s + 0.0f;
       v[i] = s;
       const u64 kk = ((u64)ordered_key(s) << 32) | (bin_lo + i);
       kmin = u64min(kmin, kk); kmax = u64max(kmax, kk);

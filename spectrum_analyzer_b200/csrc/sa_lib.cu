@@ -643,21 +643,35 @@ int sa_spectrum_single(sa_ctx *ctx, const float *h_samples, uint64_t n_samples, 
   return SA_OK;
 }
 
-int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint32_t n_bins, uint64_t stride,
-                             uint32_t bin_lo, uint32_t n, int scaling_kind, uint32_t stats_mask,
-                             sa_frame_stats *d_stats) {
+int sa_apply_scaling_chain_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint32_t n_bins, uint64_t stride,
+                                   uint32_t bin_lo, uint32_t n, const int *scaling_kinds, uint32_t n_kinds,
+                                   uint32_t stats_mask, sa_frame_stats *d_stats) {
   if (!ctx || !d_vals || !d_stats || n_bins < 2 || stride < n_bins || n < 2) return SA_ERR_INVALID_ARGUMENT;
-  if (scaling_kind < SA_SCALING_NONE || scaling_kind > SA_SCALING_20_TIMES_LOG10) return SA_ERR_INVALID_ARGUMENT;
+  if (n_kinds > 8 || (n_kinds && !scaling_kinds)) return SA_ERR_INVALID_ARGUMENT;
+  sa::ScalingChain chain;
+  chain.count = (int)n_kinds;
+  const float nf = (float)n;
+  for (uint32_t c = 0; c < 8; c++) {
+    const int k = c < n_kinds ? scaling_kinds[c] : SA_SCALING_NONE;
+    if (k < SA_SCALING_NONE || k > SA_SCALING_20_TIMES_LOG10) return SA_ERR_INVALID_ARGUMENT;
+    chain.kind[c] = k;
+    chain.div[c] = k == SA_SCALING_DIVIDE_BY_N_SQRT ? sqrtf(nf) : nf;
+  }
   if (n_frames == 0) return SA_OK;
   SA_CUDA(cudaSetDevice(ctx->device));
-  const float nf = (float)n;
-  const float div = scaling_kind == SA_SCALING_DIVIDE_BY_N_SQRT ? sqrtf(nf) : nf;
   const unsigned grid = (unsigned)std::min<uint64_t>(n_frames, (uint64_t)ctx->num_sms * 8);
-  sa::rescale_kernel<<<grid, sa::RESCALE_THREADS, 0, ctx->stream>>>(d_vals, n_frames, n_bins, stride, bin_lo, scaling_kind,
-                                                                    div, stats_mask & SA_STATS_ALL, d_stats);
+  sa::rescale_kernel<<<grid, sa::RESCALE_THREADS, 0, ctx->stream>>>(d_vals, n_frames, n_bins, stride, bin_lo, chain,
+                                                                    stats_mask & SA_STATS_ALL, d_stats);
   ctx->launches++;
   SA_CUDA(cudaGetLastError());
   return SA_OK;
+}
+
+int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint32_t n_bins, uint64_t stride,
+                             uint32_t bin_lo, uint32_t n, int scaling_kind, uint32_t stats_mask,
+                             sa_frame_stats *d_stats) {
+  return sa_apply_scaling_chain_batched(ctx, d_vals, n_frames, n_bins, stride, bin_lo, n, &scaling_kind, 1, stats_mask,
+                                        d_stats);
 }
 
 int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t n_frames, uint32_t n,

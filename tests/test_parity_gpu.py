@@ -247,3 +247,30 @@ def test_apply_scaling_batched_repeated(gpu_ctx):
         s = O.calc_statistics(spec.values())
         assert (s.min_val, s.max_val, s.median) == (spec.min()[1], spec.max()[1], spec.median())
     assert np.abs(spec.values() * np.float32(n) ** 1.5 - ref.vals).max() <= MAG_RTOL * ref.vals.max()
+
+
+def test_combined_scaling_chain(gpu_ctx):
+    """scaling::combined (src/scaling.rs:174-182): the whole chain sees the SAME pre-call statistics."""
+    m = sa()
+    n = 1024
+    x = noise(1, n, seed=31, amp=300.0)
+    w = O.window_apply(O.WINDOW_HANN, x)
+    for chain_gpu, chain_cpu in [
+        ([m.scaling.divide_by_N, m.scaling.scale_20_times_log10], [O.SCALING_DIVIDE_BY_N, O.SCALING_20_TIMES_LOG10]),
+        ([m.scaling.scale_20_times_log10, m.scaling.divide_by_N, m.scaling.divide_by_N_sqrt],
+         [O.SCALING_20_TIMES_LOG10, O.SCALING_DIVIDE_BY_N, O.SCALING_DIVIDE_BY_N_SQRT]),      # scaling.rs:214
+        ([m.scaling.scale_to_zero_to_one, m.scaling.scale_to_zero_to_one], [O.SCALING_ZERO_TO_ONE] * 2),
+    ]:
+        spec = m.samples_fft_to_spectrum(w, 44100, m.FrequencyLimit.All, None)
+        before = spec.values().copy()
+        pre = O.calc_statistics(before)
+        spec.apply_scaling_fn(m.scaling.combined(chain_gpu))
+        want = before.copy()
+        for k in chain_cpu:   # every step with the statistics of the spectrum BEFORE the call
+            want = np.array([O.scale(k, v, pre.min_val, pre.max_val, pre.average, pre.median, np.float32(n)) for v in want],
+                            np.float32)
+        assert np.array_equal(spec.values(), want)
+        s = O.calc_statistics(spec.values())
+        assert (s.min_val, s.max_val, s.median) == (spec.min()[1], spec.max()[1], spec.median())
+    with pytest.raises(TypeError):
+        m.scaling.combined([m.scaling.divide_by_N, lambda v, s: v])
