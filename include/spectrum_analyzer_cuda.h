@@ -158,6 +158,15 @@ int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, 
                         uint32_t stats_mask, float *d_out_vals, uint64_t out_stride,
                         sa_frame_stats *d_stats, uint32_t *bin_lo, uint32_t *n_bins);
 
+/* Same call on int16 PCM: each sample is converted exactly (`x as f32`, as the reference's callers do,
+ * src/tests/mod.rs:70-73) when it is loaded, so the conversion never touches memory.  frame_stride counts
+ * samples. */
+int sa_spectrum_batched_i16(sa_ctx *ctx, const int16_t *d_samples, uint64_t n_frames, uint32_t n,
+                            uint64_t frame_stride, uint32_t sampling_rate, int limit_kind,
+                            float limit_lo, float limit_hi, int window_kind, int scaling_kind,
+                            uint32_t stats_mask, float *d_out_vals, uint64_t out_stride,
+                            sa_frame_stats *d_stats, uint32_t *bin_lo, uint32_t *n_bins);
+
 /* Same call with HOST buffers: pinned staging, chunked H2D -> kernel -> D2H pipeline
  * on the context's copy streams; synchronous.  This is the end-to-end form a drop-in
  * caller with host data uses. */
@@ -166,6 +175,12 @@ int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_fra
                              float limit_lo, float limit_hi, int window_kind, int scaling_kind,
                              uint32_t stats_mask, float *h_out_vals, uint64_t out_stride,
                              sa_frame_stats *h_stats, uint32_t *bin_lo, uint32_t *n_bins);
+
+int sa_spectrum_batched_host_i16(sa_ctx *ctx, const int16_t *h_samples, uint64_t n_frames, uint32_t n,
+                                 uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                                 float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
+                                 float *h_out_vals, uint64_t out_stride, sa_frame_stats *h_stats,
+                                 uint32_t *bin_lo, uint32_t *n_bins);
 
 /* Single-frame drop-in for `samples_fft_to_spectrum(samples, sampling_rate, limit,
  * scaling_fn)` (src/lib.rs:157-162): host in, host out, full error taxonomy with the

@@ -47,18 +47,25 @@ def main():
         ("64 hann all none", 64, 64, 32 * 1024 * 1024, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
         ("512 hann all none", 512, 512, 8 * 1024 * 1024, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
         ("32768 hann all none", 32768, 32768, 65_536, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
+        ("i16 cfg2 4096 hann all div_sqrt", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All, cabi.SCALING_DIVIDE_BY_N_SQRT, 7),
+        ("i16 cfg3 2048 hamming hop512", 2048, 512, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
     ]
     for name, n, hop, frames, win, lim, sc, st in configs:
+        i16 = name.startswith("i16")
         frames = max(1024, int(frames * args.scale))
         nsamp = (frames - 1) * hop + n
         x = torch.empty(nsamp, dtype=torch.float32, device=dev)
         chk(lib.sa_generate_noise(ctx._h, x.data_ptr(), 0, nsamp, 0x5A17))
+        if i16:
+            x = (x * 8192.0).clamp_(-32768, 32767).to(torch.int16)
+        entry = lib.sa_spectrum_batched_i16 if i16 else lib.sa_spectrum_batched
+        esz = 2 if i16 else 4
         bin_lo, n_bins = lim.to_bins(n, 44100)
         vals = torch.empty(frames * n_bins, dtype=torch.float32, device=dev)
         stats = torch.empty(frames * 32, dtype=torch.uint8, device=dev)
 
         def step():
-            chk(lib.sa_spectrum_batched(ctx._h, x.data_ptr(), frames, n, hop, 44100, lim.kind, lim.lo, lim.hi, win, sc, st,
+            chk(entry(ctx._h, x.data_ptr(), frames, n, hop, 44100, lim.kind, lim.lo, lim.hi, win, sc, st,
                                         vals.data_ptr(), n_bins, stats.data_ptr(), None, None))
         for _ in range(3):
             step()
@@ -70,7 +77,7 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        bpf = 4 * hop + 4 * n_bins + 32
+        bpf = esz * hop + 4 * n_bins + 32
         fps = frames / (ms * 1e-3)
         ok = int((stats.view(torch.int32).view(frames, 8)[:, 6] != 0).sum().item()) == 0
         print(json.dumps({"config": name, "n": n, "hop": hop, "frames": frames, "n_bins": n_bins, "ms": round(ms, 4),

@@ -42,7 +42,17 @@ extern "C" {
                                window_kind: c_int, scaling_kind: c_int, stats_mask: u32, d_out_vals: *mut f32,
                                out_stride: u64, d_stats: *mut sa_frame_stats, bin_lo: *mut u32,
                                n_bins: *mut u32) -> c_int;
+    pub fn sa_spectrum_batched_i16(ctx: *mut sa_ctx, d_samples: *const i16, n_frames: u64, n: u32, frame_stride: u64,
+                               sampling_rate: u32, limit_kind: c_int, limit_lo: f32, limit_hi: f32,
+                               window_kind: c_int, scaling_kind: c_int, stats_mask: u32, d_out_vals: *mut f32,
+                               out_stride: u64, d_stats: *mut sa_frame_stats, bin_lo: *mut u32,
+                               n_bins: *mut u32) -> c_int;
     pub fn sa_spectrum_batched_host(ctx: *mut sa_ctx, h_samples: *const f32, n_frames: u64, n: u32,
+                                    frame_stride: u64, sampling_rate: u32, limit_kind: c_int, limit_lo: f32,
+                                    limit_hi: f32, window_kind: c_int, scaling_kind: c_int, stats_mask: u32,
+                                    h_out_vals: *mut f32, out_stride: u64, h_stats: *mut sa_frame_stats,
+                                    bin_lo: *mut u32, n_bins: *mut u32) -> c_int;
+    pub fn sa_spectrum_batched_host_i16(ctx: *mut sa_ctx, h_samples: *const i16, n_frames: u64, n: u32,
                                     frame_stride: u64, sampling_rate: u32, limit_kind: c_int, limit_lo: f32,
                                     limit_hi: f32, window_kind: c_int, scaling_kind: c_int, stats_mask: u32,
                                     h_out_vals: *mut f32, out_stride: u64, h_stats: *mut sa_frame_stats,

@@ -64,6 +64,10 @@ SYMBOLS = {
                                  _u32p, _u32p]),
     "sa_spectrum_batched_host": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _i, _f, _f, _i, _i, _u32, _vp, _u64, _vp,
                                       _u32p, _u32p]),
+    "sa_spectrum_batched_i16": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _i, _f, _f, _i, _i, _u32, _vp, _u64, _vp,
+                                     _u32p, _u32p]),
+    "sa_spectrum_batched_host_i16": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _i, _f, _f, _i, _i, _u32, _vp, _u64, _vp,
+                                          _u32p, _u32p]),
     "sa_spectrum_single": (_i, [_vp, _vp, _u64, _u32, _i, _f, _f, _i, _i, _vp, _vp, _u32p, _vp]),
     "sa_apply_scaling_batched": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _u32, _i, _u32, _vp]),
     "sa_apply_scaling_chain_batched": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _u32, _vp, _u32, _u32, _vp]),

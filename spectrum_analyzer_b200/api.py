@@ -399,6 +399,8 @@ def samples_fft_to_spectrum_batched(frames, sampling_rate: int, frequency_limit:
     * numpy input  -> host pipeline (``sa_spectrum_batched_host``), numpy output
     * torch CUDA input -> device-resident call on torch's current stream (``sa_spectrum_batched``),
       torch output; asynchronous.
+    * int16 input (numpy or torch) is PCM: converted `x as f32` inside the kernel's load
+      (``sa_spectrum_batched_i16`` / ``sa_spectrum_batched_host_i16``), halving the input traffic.
     """
     kind = _scaling_kind(scaling_fn)
     wk = _window_kind(window)
@@ -419,22 +421,25 @@ def samples_fft_to_spectrum_batched(frames, sampling_rate: int, frequency_limit:
 
     if _is_torch(frames):
         import torch
-        assert frames.is_cuda and frames.dtype == torch.float32 and frames.is_contiguous()
+        assert frames.is_cuda and frames.dtype in (torch.float32, torch.int16) and frames.is_contiguous()
+        entry = lib.sa_spectrum_batched_i16 if frames.dtype == torch.int16 else lib.sa_spectrum_batched
         dev = frames.device
         if ctx is None:
             ctx = _torch_ctx(dev.index or 0, torch.cuda.current_stream(dev).cuda_stream)
         vals = out if out is not None else torch.empty((n_frames, stride), dtype=torch.float32, device=dev)
         st = out_stats if out_stats is not None else torch.empty((n_frames, 32), dtype=torch.uint8, device=dev)
-        _check(lib.sa_spectrum_batched(ctx._h, frames.data_ptr(), n_frames, n, frame_stride, sampling_rate,
+        _check(entry(ctx._h, frames.data_ptr(), n_frames, n, frame_stride, sampling_rate,
                                        frequency_limit.kind, frequency_limit.lo, frequency_limit.hi, wk, kind, stats,
                                        vals.data_ptr(), stride, st.data_ptr() if stats else None, None, None))
         return BatchedSpectrum(vals, st, freqs, bin_lo, n_bins, n, sampling_rate)
 
-    x = np.ascontiguousarray(frames, dtype=np.float32)
+    is_i16 = isinstance(frames, np.ndarray) and frames.dtype == np.int16
+    x = np.ascontiguousarray(frames) if is_i16 else np.ascontiguousarray(frames, dtype=np.float32)
+    host_entry = lib.sa_spectrum_batched_host_i16 if is_i16 else lib.sa_spectrum_batched_host
     ctx = ctx or default_context()
     vals = out if out is not None else np.zeros((n_frames, stride), np.float32)
     st = out_stats if out_stats is not None else np.zeros(n_frames, A.FRAME_STATS_DTYPE)
-    _check(lib.sa_spectrum_batched_host(ctx._h, x.ctypes.data, n_frames, n, frame_stride, sampling_rate,
+    _check(host_entry(ctx._h, x.ctypes.data, n_frames, n, frame_stride, sampling_rate,
                                         frequency_limit.kind, frequency_limit.lo, frequency_limit.hi, wk, kind, stats,
                                         vals.ctypes.data, stride, st.ctypes.data if stats else None, None, None))
     return BatchedSpectrum(vals, st, freqs, bin_lo, n_bins, n, sampling_rate)

@@ -17,11 +17,11 @@ __global__ void __launch_bounds__(128) spectrum_tiny_kernel(const SpectrumParams
   const u64 frame = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (frame >= p.n_frames) return;
   const int n = 1 << log2n, m = n >> 1;
-  const float *src = p.samples + frame * p.frame_stride;
+  const u64 base = frame * p.frame_stride;
   float2 z[16];
   uint32_t flags = 0;
   for (int i = 0; i < m; i++) {
-    float a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+    float a = load_sample(p, base + 2 * i), b = load_sample(p, base + 2 * i + 1);
     if (p.window) { a = __fmul_rn(__ldg(p.window + 2 * i), a); b = __fmul_rn(__ldg(p.window + 2 * i + 1), b); }
     flags |= (a != a || b != b) ? 1u : 0u;
     flags |= (fabsf(a) == INFINITY || fabsf(b) == INFINITY) ? 2u : 0u;

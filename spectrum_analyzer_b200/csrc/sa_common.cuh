@@ -23,8 +23,33 @@ struct SpectrumParams {
   int scaling_kind;
   uint32_t stats_mask;
   float scale_div;            // stats.n (divide_by_N) or sqrtf(stats.n) (divide_by_N_sqrt)
-  int aligned8;               // samples base and frame_stride allow 8-byte loads
+  int aligned8;               // samples base and frame_stride allow pair loads (8 B for f32, 4 B for i16)
+  int in_i16;                 // samples are int16 PCM (converted exactly, `x as f32`, when loaded)
 };
+
+// ---- sample loads: f32, or int16 PCM converted on the fly (the reference's callers do `x as f32`,
+// src/tests/mod.rs:70-73, examples/mp3-samples.rs:94) --------------------------------------------------
+__device__ __forceinline__ float load_sample(const SpectrumParams &p, u64 idx) {
+  if (p.in_i16) return (float)__ldg(reinterpret_cast<const short *>(p.samples) + idx);
+  return __ldg(p.samples + idx);
+}
+// E complex pairs (samples 2n, 2n+1 with n = j + s*T) of the frame starting at element `base`;
+// requires pair alignment.  The element-type branch is hoisted out of the unrolled loops.
+template <int E, int T>
+__device__ __forceinline__ void load_frame_pairs(float2 (&x)[E], const SpectrumParams &p, u64 base, int j) {
+  if (p.in_i16) {
+    const short2 *src = reinterpret_cast<const short2 *>(reinterpret_cast<const short *>(p.samples) + base);
+#pragma unroll
+    for (int s = 0; s < E; s++) {
+      const short2 v = __ldg(src + (j + s * T));
+      x[s] = make_float2((float)v.x, (float)v.y);
+    }
+  } else {
+    const float2 *src = reinterpret_cast<const float2 *>(p.samples + base);
+#pragma unroll
+    for (int s = 0; s < E; s++) x[s] = __ldg(src + (j + s * T));
+  }
+}
 
 // ---- order-preserving float <-> u32 key (total order of OrderableF32, src/frequency.rs:64-75;
 // -0.0 == +0.0 there, so -0.0 is canonicalised first) -------------------------------------------

@@ -325,13 +325,14 @@ int validate_call(uint64_t n, uint32_t sampling_rate, int limit_kind, float lo, 
   return SA_OK;
 }
 
-int fill_params(sa_ctx *ctx, SpectrumParams &p, const float *d_samples, uint64_t n_frames, uint32_t n,
+int fill_params(sa_ctx *ctx, SpectrumParams &p, const void *d_samples, int in_i16, uint64_t n_frames, uint32_t n,
                 uint64_t frame_stride, int window_kind, int scaling_kind, uint32_t stats_mask, float *d_out,
                 uint64_t out_stride, sa_frame_stats *d_stats, uint32_t bin_lo, uint32_t n_bins) {
   int e;
   if ((e = get_twiddle(ctx, n, &p.twiddle)) != SA_OK) return e;
   if ((e = get_window(ctx, window_kind, n, &p.window)) != SA_OK) return e;
-  p.samples = d_samples;
+  p.samples = static_cast<const float *>(d_samples);
+  p.in_i16 = in_i16;
   p.out_vals = d_out;
   p.stats = (stats_mask & SA_STATS_ALL) ? d_stats : nullptr;
   p.n_frames = n_frames;
@@ -343,7 +344,8 @@ int fill_params(sa_ctx *ctx, SpectrumParams &p, const float *d_samples, uint64_t
   p.stats_mask = stats_mask & SA_STATS_ALL;
   const float nf = (float)n;  // stats.n = samples_len as f32 (src/spectrum.rs:144)
   p.scale_div = scaling_kind == SA_SCALING_DIVIDE_BY_N_SQRT ? sqrtf(nf) : nf;
-  p.aligned8 = ((reinterpret_cast<uintptr_t>(d_samples) & 7u) == 0 && (frame_stride & 1u) == 0) ? 1 : 0;
+  const uintptr_t pair_mask = in_i16 ? 3u : 7u;   // a (2n, 2n+1) sample pair must be naturally aligned
+  p.aligned8 = ((reinterpret_cast<uintptr_t>(d_samples) & pair_mask) == 0 && (frame_stride & 1u) == 0) ? 1 : 0;
   return SA_OK;
 }
 
@@ -518,10 +520,11 @@ int sa_bin_frequencies(uint32_t n, uint32_t sampling_rate, uint32_t bin_lo, uint
   return SA_OK;
 }
 
-int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, uint32_t n, uint64_t frame_stride,
-                        uint32_t sampling_rate, int limit_kind, float limit_lo, float limit_hi, int window_kind,
-                        int scaling_kind, uint32_t stats_mask, float *d_out_vals, uint64_t out_stride,
-                        sa_frame_stats *d_stats, uint32_t *bin_lo, uint32_t *n_bins) {
+static int spectrum_batched_impl(sa_ctx *ctx, const void *d_samples, int in_i16, uint64_t n_frames, uint32_t n,
+                                 uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                                 float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
+                                 float *d_out_vals, uint64_t out_stride, sa_frame_stats *d_stats, uint32_t *bin_lo,
+                                 uint32_t *n_bins) {
   if (!ctx) return SA_ERR_INVALID_ARGUMENT;
   uint32_t lo = 0, nb = 0;
   const int e = validate_call(n, sampling_rate, limit_kind, limit_lo, limit_hi, window_kind, scaling_kind, &lo, &nb);
@@ -533,17 +536,37 @@ int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, 
   if ((stats_mask & SA_STATS_ALL) && !d_stats) return SA_ERR_INVALID_ARGUMENT;
   SA_CUDA(cudaSetDevice(ctx->device));
   SpectrumParams p;
-  int pe = fill_params(ctx, p, d_samples, n_frames, n, frame_stride, window_kind, scaling_kind, stats_mask,
+  int pe = fill_params(ctx, p, d_samples, in_i16, n_frames, n, frame_stride, window_kind, scaling_kind, stats_mask,
                        d_out_vals, out_stride, d_stats, lo, nb);
   if (pe != SA_OK) return pe;
   return launch_spectrum(ctx, p, log2_exact(n));
 }
 
-int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_frames, uint32_t n,
-                             uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
-                             float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
-                             float *h_out_vals, uint64_t out_stride, sa_frame_stats *h_stats, uint32_t *bin_lo,
-                             uint32_t *n_bins) {
+int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, uint32_t n, uint64_t frame_stride,
+                        uint32_t sampling_rate, int limit_kind, float limit_lo, float limit_hi, int window_kind,
+                        int scaling_kind, uint32_t stats_mask, float *d_out_vals, uint64_t out_stride,
+                        sa_frame_stats *d_stats, uint32_t *bin_lo, uint32_t *n_bins) {
+  return spectrum_batched_impl(ctx, d_samples, 0, n_frames, n, frame_stride, sampling_rate, limit_kind, limit_lo,
+                               limit_hi, window_kind, scaling_kind, stats_mask, d_out_vals, out_stride, d_stats, bin_lo,
+                               n_bins);
+}
+
+int sa_spectrum_batched_i16(sa_ctx *ctx, const int16_t *d_samples, uint64_t n_frames, uint32_t n,
+                            uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                            float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask, float *d_out_vals,
+                            uint64_t out_stride, sa_frame_stats *d_stats, uint32_t *bin_lo, uint32_t *n_bins) {
+  return spectrum_batched_impl(ctx, d_samples, 1, n_frames, n, frame_stride, sampling_rate, limit_kind, limit_lo,
+                               limit_hi, window_kind, scaling_kind, stats_mask, d_out_vals, out_stride, d_stats, bin_lo,
+                               n_bins);
+}
+
+static int spectrum_batched_host_impl(sa_ctx *ctx, const void *h_samples_v, int in_i16, uint64_t n_frames, uint32_t n,
+                                      uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                                      float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
+                                      float *h_out_vals, uint64_t out_stride, sa_frame_stats *h_stats,
+                                      uint32_t *bin_lo, uint32_t *n_bins) {
+  const size_t esz = in_i16 ? sizeof(int16_t) : sizeof(float);
+  const unsigned char *h_samples = static_cast<const unsigned char *>(h_samples_v);
   if (!ctx) return SA_ERR_INVALID_ARGUMENT;
   uint32_t lo = 0, nb = 0;
   const int e = validate_call(n, sampling_rate, limit_kind, limit_lo, limit_hi, window_kind, scaling_kind, &lo, &nb);
@@ -558,16 +581,16 @@ int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_fra
 
   // chunking: ~64 MiB of unique input per chunk
   const uint64_t target = 64ull << 20;
-  uint64_t chunk = std::max<uint64_t>(1, target / (frame_stride * sizeof(float)));
+  uint64_t chunk = std::max<uint64_t>(1, target / (frame_stride * esz));
   chunk = std::min(chunk, n_frames);
-  const size_t in_bytes = ((chunk - 1) * frame_stride + n) * sizeof(float);
+  const size_t in_bytes = ((chunk - 1) * frame_stride + n) * esz;
   const size_t out_bytes = chunk * out_stride * sizeof(float);
   const size_t st_bytes = chunk * sizeof(sa_frame_stats);
   int pe = ensure_pipeline(ctx, in_bytes, out_bytes, st_bytes);
   if (pe != SA_OK) return pe;
 
   ScopedPin pin_in, pin_out, pin_st;
-  pin_in.pin(h_samples, ((n_frames - 1) * frame_stride + n) * sizeof(float));
+  pin_in.pin(h_samples, ((n_frames - 1) * frame_stride + n) * esz);
   pin_out.pin(h_out_vals, ((n_frames - 1) * out_stride + nb) * sizeof(float));
   if (want_stats) pin_st.pin(h_stats, n_frames * sizeof(sa_frame_stats));
 
@@ -580,12 +603,12 @@ int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_fra
       SA_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[s], 0));     // input slot consumed
       SA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));   // output slot drained
     }
-    SA_CUDA(cudaMemcpyAsync(ctx->slot_in[s], h_samples + f0 * frame_stride,
-                            ((nf - 1) * frame_stride + n) * sizeof(float), cudaMemcpyHostToDevice, ctx->h2d));
+    SA_CUDA(cudaMemcpyAsync(ctx->slot_in[s], h_samples + f0 * frame_stride * esz,
+                            ((nf - 1) * frame_stride + n) * esz, cudaMemcpyHostToDevice, ctx->h2d));
     SA_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->h2d));
     SA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
     SpectrumParams p;
-    pe = fill_params(ctx, p, ctx->slot_in[s], nf, n, frame_stride, window_kind, scaling_kind, stats_mask,
+    pe = fill_params(ctx, p, ctx->slot_in[s], in_i16, nf, n, frame_stride, window_kind, scaling_kind, stats_mask,
                      ctx->slot_out[s], out_stride, ctx->slot_stats[s], lo, nb);
     if (pe != SA_OK) return pe;
     pe = launch_spectrum(ctx, p, log2n);
@@ -603,6 +626,26 @@ int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_fra
   SA_CUDA(cudaStreamSynchronize(ctx->stream));
   SA_CUDA(cudaStreamSynchronize(ctx->h2d));
   return SA_OK;
+}
+
+int sa_spectrum_batched_host(sa_ctx *ctx, const float *h_samples, uint64_t n_frames, uint32_t n,
+                             uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                             float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
+                             float *h_out_vals, uint64_t out_stride, sa_frame_stats *h_stats, uint32_t *bin_lo,
+                             uint32_t *n_bins) {
+  return spectrum_batched_host_impl(ctx, h_samples, 0, n_frames, n, frame_stride, sampling_rate, limit_kind, limit_lo,
+                                    limit_hi, window_kind, scaling_kind, stats_mask, h_out_vals, out_stride, h_stats,
+                                    bin_lo, n_bins);
+}
+
+int sa_spectrum_batched_host_i16(sa_ctx *ctx, const int16_t *h_samples, uint64_t n_frames, uint32_t n,
+                                 uint64_t frame_stride, uint32_t sampling_rate, int limit_kind, float limit_lo,
+                                 float limit_hi, int window_kind, int scaling_kind, uint32_t stats_mask,
+                                 float *h_out_vals, uint64_t out_stride, sa_frame_stats *h_stats, uint32_t *bin_lo,
+                                 uint32_t *n_bins) {
+  return spectrum_batched_host_impl(ctx, h_samples, 1, n_frames, n, frame_stride, sampling_rate, limit_kind, limit_lo,
+                                    limit_hi, window_kind, scaling_kind, stats_mask, h_out_vals, out_stride, h_stats,
+                                    bin_lo, n_bins);
 }
 
 int sa_spectrum_single(sa_ctx *ctx, const float *h_samples, uint64_t n_samples, uint32_t sampling_rate,

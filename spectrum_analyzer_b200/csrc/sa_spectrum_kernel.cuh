@@ -165,13 +165,14 @@ __global__ void __launch_bounds__(C::NT) spectrum_kernel(const SpectrumParams p)
     float2 x[E];
     uint32_t flags = 0;  // bit0: NaN, bit1: Inf in the windowed samples, bit2: non-finite result
     {
-      const float *src = p.samples + (active ? frame : 0) * p.frame_stride;
+      const u64 base = (active ? frame : 0) * p.frame_stride;
+      if (p.aligned8) load_frame_pairs<E, T>(x, p, base, j);
 #pragma unroll
       for (int s = 0; s < E; s++) {
         const int n = j + s * T;
         float2 v;
-        if (p.aligned8) v = __ldg(reinterpret_cast<const float2 *>(src) + n);
-        else { v.x = __ldg(src + 2 * n); v.y = __ldg(src + 2 * n + 1); }
+        if (p.aligned8) v = x[s];
+        else { v.x = load_sample(p, base + 2 * n); v.y = load_sample(p, base + 2 * n + 1); }
         if (p.window != nullptr) {
           const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window) + n);
           v.x = __fmul_rn(w.x, v.x);

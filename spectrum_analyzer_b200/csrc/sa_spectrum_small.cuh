@@ -81,10 +81,8 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
 
   float2 x[E];
 #pragma unroll
-  for (int s = 0; s < E; s++) {
-    x[s] = make_float2(0.f, 0.f);
-    if (active) x[s] = __ldg(reinterpret_cast<const float2 *>(p.samples + frame * p.frame_stride) + (j + s * T));
-  }
+  for (int s = 0; s < E; s++) x[s] = make_float2(0.f, 0.f);
+  if (active) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);
 
   auto binof = [&](int i) -> uint32_t {
     const uint32_t k = (uint32_t)(j + (i >> 1) * T);
@@ -160,10 +158,8 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
     frame += fstep;
     active = frame < p.n_frames;
 #pragma unroll
-    for (int s = 0; s < E; s++) {
-      x[s] = make_float2(0.f, 0.f);
-      if (active) x[s] = __ldg(reinterpret_cast<const float2 *>(p.samples + frame * p.frame_stride) + (j + s * T));
-    }
+    for (int s = 0; s < E; s++) x[s] = make_float2(0.f, 0.f);
+    if (active) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);
     const bool more = __any_sync(0xffffffffu, active);
 
     // ---- FrequencyLimit slice ---------------------------------------------------------------------------
@@ -257,10 +253,9 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
       nonfinite = nonfinite && cur_active;
       if (__any_sync(0xffffffffu, nonfinite)) {   // rare: classify NaN / Inf in the windowed input
         if (nonfinite) {
-          const float *src = p.samples + cur * p.frame_stride;
           uint32_t f = 4u;
           for (int n = j; n < N; n += T) {
-            const float v = __fmul_rn(s_win[n], __ldg(src + n));
+            const float v = __fmul_rn(s_win[n], load_sample(p, cur * p.frame_stride + n));
             if (v != v) f |= 1u;
             if (fabsf(v) == INFINITY) f |= 2u;
           }

@@ -203,13 +203,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
 
   // ---- load of the first frame (raw samples; the window is applied at the top of the loop) ------
   float2 x[E];
-  {
-    const float *src = p.samples + frame * p.frame_stride;
-#pragma unroll
-    for (int s = 0; s < E; s++) {
-      x[s] = __ldg(reinterpret_cast<const float2 *>(src) + (j + s * T));  // 8-byte aligned (host checks)
-    }
-  }
+  load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);   // pair-aligned (the host checks)
   float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
 
   // thread 0: write the record fields of the previous frame (everything except a median written
@@ -431,11 +425,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     const u64 cur = frame;
     frame += fstep;
     const bool more = frame < p.n_frames;
-    if (more) {
-      const float *src = p.samples + frame * p.frame_stride;
-#pragma unroll
-      for (int s = 0; s < E; s++) x[s] = __ldg(reinterpret_cast<const float2 *>(src) + (j + s * T));
-    }
+    if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);
 
     // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
     uint32_t valid = 0xffffffffu;
@@ -607,10 +597,9 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       if constexpr (MODE == SCALE_LOG10 || MODE == SCALE_ZERO_ONE) nonfinite = (__float_as_uint(umax) >= 0x7f800000u);
       else nonfinite = (kmx >= 0x7f800000u);
       if (nonfinite) {  // group-uniform rare path: classify NaN / Inf in the windowed input
-        const float *src = p.samples + cur * p.frame_stride;
         uint32_t f = 4u;
         for (int n = j; n < N; n += T) {
-          const float v = __fmul_rn(win1(n), __ldg(src + n));
+          const float v = __fmul_rn(win1(n), load_sample(p, cur * p.frame_stride + n));
           if (v != v) f |= 1u;
           if (fabsf(v) == INFINITY) f |= 2u;
         }

@@ -274,3 +274,40 @@ def test_combined_scaling_chain(gpu_ctx):
         assert (s.min_val, s.max_val, s.median) == (spec.min()[1], spec.max()[1], spec.median())
     with pytest.raises(TypeError):
         m.scaling.combined([m.scaling.divide_by_N, lambda v, s: v])
+
+
+@pytest.mark.parametrize("n,hop,offset", [(8, 8, 0), (32, 16, 0), (64, 64, 0), (256, 128, 0), (512, 512, 2),
+                                          (1024, 1024, 0), (2048, 512, 0), (4096, 4096, 0), (4096, 1001, 0),
+                                          (4096, 4096, 1), (8192, 8192, 0), (16384, 16384, 0), (32768, 32768, 0)])
+def test_int16_ingestion_equals_f32_path(gpu_ctx, n, hop, offset):
+    """Fused i16 PCM ingestion (`x as f32` on load, reference callers: src/tests/mod.rs:70-73) must give the
+    very same bits as converting on the host and calling the f32 entry point -- in every kernel family, for
+    aligned and unaligned (odd hop / odd offset) inputs, on the device and through the host pipeline."""
+    import torch
+    m = sa()
+    rng = np.random.default_rng(n + hop)
+    frames = 37
+    pcm = rng.integers(-32768, 32768, size=offset + (frames - 1) * hop + n, dtype=np.int16)
+    pcm[:4] = [-32768, 32767, 0, -1]
+    pcm = pcm[offset:]
+    lim = m.FrequencyLimit.All
+    kw = dict(window=O.WINDOW_HANN, n=n, frame_stride=hop, n_frames=frames, stats=7)
+    full = torch.from_numpy(np.concatenate([np.zeros(offset, np.int16), pcm])).cuda()
+    # same misalignment for the f32 arm, so that both arms dispatch to the same kernel family
+    ref = m.samples_fft_to_spectrum_batched(full.to(torch.float32)[offset:], 44100, lim,
+                                            m.scaling.divide_by_N_sqrt, **kw)
+    got = m.samples_fft_to_spectrum_batched(full[offset:], 44100, lim, m.scaling.divide_by_N_sqrt, **kw)
+    torch.cuda.synchronize()
+    assert np.array_equal(ref.vals.cpu().numpy().view(np.uint32), got.vals.cpu().numpy().view(np.uint32))
+    assert ref.stats_numpy().tobytes() == got.stats_numpy().tobytes()
+    if offset == 0:  # the host pipeline's slots are always aligned
+        host = m.samples_fft_to_spectrum_batched(pcm, 44100, lim, m.scaling.divide_by_N_sqrt, **kw)
+        assert np.array_equal(host.vals.view(np.uint32), got.vals.cpu().numpy().view(np.uint32))
+        assert host.stats.tobytes() == got.stats_numpy().tobytes()
+    # and against the oracle fed the converted samples
+    x = pcm.astype(np.float32)
+    code, ov, _, ostatus, _ = O.spectrum_batched(x, frames, n, hop, 44100, O.LIMIT_ALL, 0.0, 0.0, O.WINDOW_HANN,
+                                                 O.SCALING_DIVIDE_BY_N_SQRT)
+    assert code == 0 and np.all(ostatus == 0)
+    gv = got.vals.cpu().numpy()[:, : got.n_bins]
+    assert np.all(np.abs(gv - ov) <= MAG_RTOL * ov.max(axis=1, keepdims=True))
