@@ -29,6 +29,7 @@
 #pragma once
 #include "sa_common.cuh"
 #include "sa_dft.cuh"
+#include "sa_tmem.cuh"
 
 namespace sa {
 
@@ -59,16 +60,22 @@ struct V2Cfg {
   static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
   // big frames keep the window and the large twiddle tables in global memory (L1/L2, coalesced)
   static constexpr bool GLOBAL_TABLES = FOUR;
+  // everything else keeps the per-thread constants (window multipliers, pass twiddles, recombination
+  // twiddles: 112 words per thread) in tensor memory, read with tcgen05.ld (sa_tmem.cuh): column
+  // layout [0,32) window | [32,62) pass-2 twiddles | [64,94) last-pass twiddles | [96,112) recombination.
+  // A thread's lane is 32*(warp%4)+lane_id; groups wider than 128 threads use T/128 column sets.
+  static constexpr bool TMEM_TABLES = !FOUR;
+  static constexpr int TM_SETS = T > 128 ? T / 128 : 1, TM_SET_COLS = 128, TM_COLS = TM_SETS * TM_SET_COLS;
+  static constexpr int TM_WIN = 0, TM_TW2 = 32, TM_TW3 = 64, TM_TWR = 96;
   static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2, NTW4 = FOUR ? (R4 - 1) * 4096 : 0;
-  static constexpr int S_WIN = GLOBAL_TABLES ? 0 : N, S_TWR = GLOBAL_TABLES ? 0 : NTWR;
+  static constexpr int S_TW2 = TMEM_TABLES ? 0 : NTW2, S_TW3 = TMEM_TABLES ? 0 : NTW3;
   static_assert(T % 32 == 0 && T >= 32 && T <= 512, "v2 covers N = 1024..16384");
   static_assert(NT <= 1024 && (T == 32 || G_ <= 15), "named barriers 1..15");
   // shared memory map (bytes)
-  static constexpr size_t OFF_WIN = 0;
-  static constexpr size_t OFF_TW2 = OFF_WIN + sizeof(float) * S_WIN;
-  static constexpr size_t OFF_TW3 = OFF_TW2 + sizeof(float2) * NTW2;
-  static constexpr size_t OFF_TWR = OFF_TW3 + sizeof(float2) * NTW3;
-  static constexpr size_t OFF_GROUPS = OFF_TWR + sizeof(float2) * S_TWR;
+  static constexpr size_t OFF_TMSLOT = 0;                                  // TMEM base address (16 B slot)
+  static constexpr size_t OFF_TW2 = 16;
+  static constexpr size_t OFF_TW3 = OFF_TW2 + sizeof(float2) * S_TW2;
+  static constexpr size_t OFF_GROUPS = OFF_TW3 + sizeof(float2) * S_TW3;
   static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
   static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
   static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
@@ -133,18 +140,16 @@ __device__ __forceinline__ float div_const(float v, float d, float rd) {
 }
 
 template <class C, int MODE, bool FULL>
-__global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P) {
+__device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned char *smem, const uint32_t tm_base) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, G = C::G, NW = C::NW, R3 = C::R3, NB3 = C::NB3;
   constexpr int PADT = T + T / 16;  // padded stride of the strided reads (first exchange only)
   // N = 4096: thread j runs the two last-pass butterflies j and 256-j (thread 0: 0 and 128), whose
   // outputs are exactly each other's mirror bins Z[k] <-> Z[M-k]: the real-FFT recombination then
   // needs no exchange and no barrier.
   constexpr bool MIRROR = (NB3 == 2);
-  extern __shared__ __align__(16) unsigned char smem[];
-  float *s_win = reinterpret_cast<float *>(smem + C::OFF_WIN);
-  float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);
-  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + C::OFF_TW3);
-  float2 *s_twr = reinterpret_cast<float2 *>(smem + C::OFF_TWR);
+  constexpr bool TM = C::TMEM_TABLES;
+  float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);   // !TM only
+  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + C::OFF_TW3);   // !TM only
 
   const SpectrumParams &p = P.b;
   const int tid = threadIdx.x;
@@ -166,30 +171,71 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   uint32_t pend_kmn = 0, pend_kmx = 0, pend_medkey = 0;
   float pend_sum = 0.f;
 
-  // ---- one-time: tables -> shared memory, histogram cleared ------------------------------------
+  // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
-  if constexpr (!C::GLOBAL_TABLES)
-    for (int i = tid; i < N; i += C::NT) s_win[i] = has_win ? __ldg(p.window + i) : 1.0f;
-  for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
-  for (int i = tid; i < C::NTW3; i += C::NT) s_tw3[i] = __ldg(P.tw3 + i);
-  if constexpr (!C::GLOBAL_TABLES)
-    for (int i = tid; i < C::NTWR; i += C::NT) s_twr[i] = __ldg(P.twr + i);
-  // window multiplier pair / recombination twiddle: shared memory, or global memory for big frames
+  const int jbB = j ? 256 - j : 128;   // MIRROR: second last-pass butterfly of this thread
+  const uint32_t ta = tmem_addr(tm_base, tid >> 5, (j >> 7) * C::TM_SET_COLS);   // this thread's table row
+  if constexpr (TM) {
+    // the first max(T,128) threads cover every (lane quadrant, column set) once
+    if (tid < (T > 128 ? T : 128)) {
+      float v[16];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {   // window multipliers of samples 2n, 2n+1 for n = j + s*T
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+          const float2 w = has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + j + (8 * h + s) * T) : make_float2(1.f, 1.f);
+          v[2 * s] = w.x; v[2 * s + 1] = w.y;
+        }
+        tmem_st16(ta + C::TM_WIN + 16 * h, v);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {   // pass 2: w_256^(k*pp), k = 1..15
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+          const int k = 8 * h + s + 1;
+          const float2 w = k < 16 ? __ldg(P.tw2 + (k - 1) * 16 + (j & 15)) : make_float2(0.f, 0.f);
+          v[2 * s] = w.x; v[2 * s + 1] = w.y;
+        }
+        tmem_st16(ta + C::TM_TW2 + 16 * h, v);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {   // last pass: butterfly b, k = 1..R3-1 -> entry b*(R3-1) + k-1
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+          const int e = 8 * h + s;
+          float2 w = make_float2(0.f, 0.f);
+          if (e < NB3 * (R3 - 1)) {
+            const int b = e / (R3 - 1), k = e % (R3 - 1) + 1;
+            const int jb = MIRROR ? (b ? jbB : j) : j + b * T;
+            w = __ldg(P.tw3 + (k - 1) * 256 + jb);
+          }
+          v[2 * s] = w.x; v[2 * s + 1] = w.y;
+        }
+        tmem_st16(ta + C::TM_TW3 + 16 * h, v);
+      }
+#pragma unroll
+      for (int s = 0; s < 8; s++) {   // recombination twiddles W_N^k of the 8 bin pairs this thread owns
+        const int k = MIRROR ? ((s & 1) ? jbB : j) + 256 * (s >> 1) : j + s * T;
+        const float2 w = __ldg(P.twr + k);
+        v[2 * s] = w.x; v[2 * s + 1] = w.y;
+      }
+      tmem_st16(ta + C::TM_TWR, v);
+    }
+    tmem_fence_before_sync();
+  } else {
+    for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
+    for (int i = tid; i < C::NTW3; i += C::NT) s_tw3[i] = __ldg(P.tw3 + i);
+  }
+  // window multiplier pair / recombination twiddle from global memory (N = 16384, and the rare paths)
   auto win2 = [&](int n) -> float2 {   // multipliers of samples 2n, 2n+1
-    if constexpr (C::GLOBAL_TABLES) return has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + n) : make_float2(1.f, 1.f);
-    else return *reinterpret_cast<const float2 *>(s_win + 2 * n);
+    return has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + n) : make_float2(1.f, 1.f);
   };
-  auto win1 = [&](int n) -> float {
-    if constexpr (C::GLOBAL_TABLES) return has_win ? __ldg(p.window + n) : 1.0f;
-    else return s_win[n];
-  };
-  auto twr_at = [&](int k) -> float2 {
-    if constexpr (C::GLOBAL_TABLES) return __ldg(P.twr + k);
-    else return s_twr[k];
-  };
+  auto win1 = [&](int n) -> float { return has_win ? __ldg(p.window + n) : 1.0f; };
+  auto twr_at = [&](int k) -> float2 { return __ldg(P.twr + k); };
   for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
   if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
   __syncthreads();
+  if constexpr (TM) tmem_fence_after_sync();
 
   const uint32_t lo = p.bin_lo, hi = p.bin_hi;
   const uint32_t count = hi - lo + 1;
@@ -233,13 +279,23 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   for (;;) {
 
     // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
+    // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
+    // skip the rounding of the windowed sample that the reference performs (src/windows.rs:47)
+    if constexpr (TM) {
+      float w[32];
+      tmem_ld32(ta + C::TM_WIN, w);
 #pragma unroll
-    for (int s = 0; s < E; s++) {
-      const float2 w = win2(j + s * T);
-      // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
-      // skip the rounding of the windowed sample that the reference performs (src/windows.rs:47)
-      x[s].x = __fmul_rn(w.x, x[s].x);
-      x[s].y = __fmul_rn(w.y, x[s].y);
+      for (int s = 0; s < E; s++) {
+        x[s].x = __fmul_rn(w[2 * s], x[s].x);
+        x[s].y = __fmul_rn(w[2 * s + 1], x[s].y);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+        const float2 w = win2(j + s * T);
+        x[s].x = __fmul_rn(w.x, x[s].x);
+        x[s].y = __fmul_rn(w.y, x[s].y);
+      }
     }
 
     // ---- pass 1: radix 16, NS = 1 (no twiddles) -------------------------------------------------
@@ -259,7 +315,12 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     { float2 *t = wbuf; wbuf = obuf; obuf = t; }
 
     // ---- pass 2: radix 16, NS = 16 ---------------------------------------------------------------
-    {
+    if constexpr (TM) {
+      float t[32];
+      tmem_ld32(ta + C::TM_TW2, t);
+#pragma unroll
+      for (int k = 1; k < 16; k++) x[k] = cmul(x[k], make_float2(t[2 * (k - 1)], t[2 * (k - 1) + 1]));
+    } else {
       const int pp = j & 15;
 #pragma unroll
       for (int k = 1; k < 16; k++) x[k] = cmul(x[k], s_tw2[(k - 1) * 16 + pp]);
@@ -274,7 +335,6 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
     group_sync<T>(g);
     float val[E];        // magnitudes of the 16 bins this thread owns (bin index: binof(i))
     float vmid = 0.f;    // bin M/2, thread 0 only
-    const int jbB = j ? 256 - j : 128;   // MIRROR: second butterfly of this thread
     if constexpr (MIRROR) {
       // ---- pass 3 (last): two radix-8 butterflies, jbA = j -> x[0..7], jbB -> x[8..15] ------------
 #pragma unroll
@@ -283,11 +343,17 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       {
         float2 va[8], vb[8];
         va[0] = x[0]; vb[0] = x[8];
+        {
+          float t[32];
+          tmem_ld32(ta + C::TM_TW3, t);   // entries 0..6: butterfly j, 7..13: butterfly jbB
 #pragma unroll
-        for (int k = 1; k < 8; k++) {
-          va[k] = cmul(x[k], s_tw3[(k - 1) * 256 + j]);
-          vb[k] = cmul(x[8 + k], s_tw3[(k - 1) * 256 + jbB]);
+          for (int k = 1; k < 8; k++) {
+            va[k] = cmul(x[k], make_float2(t[2 * (k - 1)], t[2 * (k - 1) + 1]));
+            vb[k] = cmul(x[8 + k], make_float2(t[2 * (k + 6)], t[2 * (k + 6) + 1]));
+          }
         }
+        float tr[16];
+        tmem_ld16(ta + C::TM_TWR, tr);    // W_N^k of the pairs (j + 256 q), (jbB + 256 q)
         dft8(va);     // va[q] = Z[j   + 256 q]
         dft8(vb);     // vb[q] = Z[jbB + 256 q]
         // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ----
@@ -305,10 +371,10 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         for (int q = 0; q < 4; q++) {
           // kA = j + 256 q pairs with M - kA: held in vb[7-q] (thread 0: its own va[8-q])
           const float2 p1 = t0 ? va[(8 - q) & 7] : vb[7 - q];
-          pair_mag(va[q], p1, twr_at(j + 256 * q), val[4 * q], val[4 * q + 1]);
+          pair_mag(va[q], p1, make_float2(tr[4 * q], tr[4 * q + 1]), val[4 * q], val[4 * q + 1]);
           // kB = jbB + 256 q pairs with M - kB: held in va[7-q] (thread 0: its own vb[7-q])
           const float2 p2 = t0 ? vb[7 - q] : va[7 - q];
-          pair_mag(vb[q], p2, twr_at(jbB + 256 * q), val[4 * q + 2], val[4 * q + 3]);
+          pair_mag(vb[q], p2, make_float2(tr[4 * q + 2], tr[4 * q + 3]), val[4 * q + 2], val[4 * q + 3]);
         }
         if (t0) {
           val[0] = 2.0f * fabsf(va[0].x + va[0].y);                         // X[0]   = Zr + Zi
@@ -359,14 +425,18 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
         }
       } else {
         // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
+        float t[32];
+        tmem_ld32(ta + C::TM_TW3, t);     // entry b*(R3-1) + k-1
 #pragma unroll
         for (int b = 0; b < NB3; b++) {
           float2 v[R3];
 #pragma unroll
           for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
-          const int jb = j + b * T;  // < 256
 #pragma unroll
-          for (int k = 1; k < R3; k++) v[k] = cmul(v[k], s_tw3[(k - 1) * 256 + jb]);
+          for (int k = 1; k < R3; k++) {
+            const int e = b * (R3 - 1) + k - 1;
+            v[k] = cmul(v[k], make_float2(t[2 * e], t[2 * e + 1]));
+          }
           dft<R3>(v);
 #pragma unroll
           for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
@@ -385,11 +455,13 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
       {
         // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
         const float2 *r = wbuf + (M / 2 - j);
+        float tr[16];
+        if constexpr (TM) tmem_ld16(ta + C::TM_TWR, tr);
 #pragma unroll
         for (int s = 0; s < E / 2; s++) {
           const float2 a = x[s];
           const float2 bq = r[-s * T];
-          const float2 w = twr_at(j + s * T);
+          const float2 w = TM ? make_float2(tr[2 * s], tr[2 * s + 1]) : twr_at(j + s * T);
           // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
           const float2 cb = make_float2(bq.x, -bq.y);
           const float2 pp = add2(a, cb), qq = sub2(a, cb);
@@ -891,6 +963,27 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   if (want_stats) {
     group_sync<T>(g);                 // every thread of the group has finished its last frame
     if (j == 0) flush_record();
+  }
+}
+
+template <class C, int MODE, bool FULL>
+__global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t tm_base = 0;
+  if constexpr (C::TMEM_TABLES) {
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + C::OFF_TMSLOT);
+    if (threadIdx.x < 32) tmem_alloc<C::TM_COLS>(slot);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    tm_base = *slot;
+  }
+  spectrum_body_v2<C, MODE, FULL>(P, smem, tm_base);
+  if constexpr (C::TMEM_TABLES) {
+    // groups finish at different times: the allocation is released once every thread is done with it
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<C::TM_COLS>(tm_base);
   }
 }
 

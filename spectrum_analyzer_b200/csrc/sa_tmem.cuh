@@ -1,0 +1,64 @@
+// sa_tmem.cuh -- tensor memory (TMEM) as a per-thread read-only table store.
+//
+// The fused spectrum kernel is bound by the LSU/shared-memory data pipe (profiles/README.md), and a
+// quarter of that traffic is per-thread constants that never change from frame to frame: the window
+// multipliers of the 32 samples a thread owns, its pass twiddles and its recombination twiddles.
+// Blackwell's tensor memory is 128 lanes x 512 columns x 32 bit per SM with its own datapath:
+// with the 32x32b shape, thread t of a warp reads / writes lane 32*(warp%4)+t, consecutive columns
+// into consecutive registers.  That is exactly a per-thread private array, and reading it does not
+// touch the shared-memory pipe (profiles/microbench/tmem_ld.cu: LDS alone 128 B/clk/SM, LDTM alone
+// 185 B/clk/SM, both together 245 B/clk/SM).  No tensor-core instruction is involved.
+#pragma once
+#include <cstdint>
+
+namespace sa {
+
+// One warp allocates NCOLS columns (power of two >= 32); the base address lands in *smem_slot.
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+               :: "r"((uint32_t)__cvta_generic_to_shared(smem_slot)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t base) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(base), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// Address of column `col` in this warp's lane quadrant.
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int warp, int col) {
+  return base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)col;
+}
+
+#define SA_R16(a) a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]
+
+// 16 / 32 consecutive columns of the calling thread's lane -> registers (waits for the data).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+               "tcgen05.wait::ld.sync.aligned;\n"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+                 "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+               "tcgen05.wait::ld.sync.aligned;\n"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+                 "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]),
+                 "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]),
+                 "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+               : "r"(taddr));
+}
+// registers -> 16 consecutive columns of the calling thread's lane (waits for completion).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+               "tcgen05.wait::st.sync.aligned;\n"
+               :: "r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+                  "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15])
+               : "memory");
+}
+
+}  // namespace sa
