@@ -12,7 +12,8 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libspectrum_analyzer_cuda.so")
+# SA_LIB_PATH: load another build of the same library (timing experiments, profiles/microbench/)
+LIB_PATH = os.environ.get("SA_LIB_PATH") or os.path.join(LIB_DIR, "libspectrum_analyzer_cuda.so")
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "spectrum_analyzer_cuda.h")
 
 NVCC_FLAGS = [

@@ -56,6 +56,7 @@ struct sa_ctx {
   bool owns_stream = false;
   uint64_t launches = 0;
   bool use_generic = false;   // SA_FORCE_GENERIC=1: run the generic kernel family for every N (A/B testing)
+  unsigned stagger_ns = 1000; // SA_STAGGER_NS: start offset between the frame groups of a v2 CTA (tuning)
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
   KernelPlan plans[16];                                     // per log2n (generic family)
@@ -190,6 +191,7 @@ int launch_v2(sa_ctx *ctx, const SpectrumParams &p) {
   P.cmul = 0.5f;
   P.div = 1.0f;
   P.rdiv = 1.0f;
+  P.stagger_ns = ctx->stagger_ns;
   switch (p.scaling_kind) {
     case SA_SCALING_NONE: break;
     case SA_SCALING_DIVIDE_BY_N: P.cmul = 0.5f / (float)C::N; break;                  // exact: N = 2^k
@@ -299,10 +301,11 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 7: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<7, 8, 16>>(ctx, p, log2n) : launch_small<SmallCfg<7>>(ctx, p);
     case 8: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n) : launch_small<SmallCfg<8>>(ctx, p);
     case 9: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n) : launch_small<SmallCfg<9>>(ctx, p);
+    // 2048..8192 stage frames with 16-byte bulk copies; frames that do not start on 16-byte boundaries take the generic family
     case 10: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, 16>>(ctx, p);
-    case 11: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
-    case 12: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
-    case 13: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
+    case 11: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
+    case 12: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
+    case 13: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
     case 14: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<14, 1>>(ctx, p);
     case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
     default: return SA_ERR_UNSUPPORTED_LENGTH;
@@ -346,6 +349,7 @@ int fill_params(sa_ctx *ctx, SpectrumParams &p, const void *d_samples, int in_i1
   p.scale_div = scaling_kind == SA_SCALING_DIVIDE_BY_N_SQRT ? sqrtf(nf) : nf;
   const uintptr_t pair_mask = in_i16 ? 3u : 7u;   // a (2n, 2n+1) sample pair must be naturally aligned
   p.aligned8 = ((reinterpret_cast<uintptr_t>(d_samples) & pair_mask) == 0 && (frame_stride & 1u) == 0) ? 1 : 0;
+  p.aligned16 = ((reinterpret_cast<uintptr_t>(d_samples) & 15u) == 0 && (frame_stride * (in_i16 ? 2u : 4u)) % 16u == 0) ? 1 : 0;
   return SA_OK;
 }
 
@@ -453,6 +457,7 @@ int sa_ctx_create_on_stream(int device, void *cuda_stream, sa_ctx **out_ctx) {
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   const char *fg = getenv("SA_FORCE_GENERIC");
   ctx->use_generic = fg && fg[0] == '1';
+  if (const char *st = getenv("SA_STAGGER_NS")) ctx->stagger_ns = (unsigned)strtoul(st, nullptr, 10);
   *out_ctx = ctx;
   return SA_OK;
 }

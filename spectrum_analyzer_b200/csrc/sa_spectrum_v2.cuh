@@ -31,6 +31,11 @@
 #include "sa_dft.cuh"
 #include "sa_tmem.cuh"
 
+// SA_EXP: timing experiments only (profiles/microbench/run_variants.sh); results are wrong when nonzero
+#ifndef SA_EXP
+#define SA_EXP 0
+#endif
+
 namespace sa {
 
 enum ScaleMode { SCALE_MUL = 0, SCALE_DIV = 1, SCALE_ZERO_ONE = 2, SCALE_LOG10 = 3 };
@@ -44,6 +49,7 @@ struct V2Params {
   float cmul;          // SCALE_MUL: 0.5/div (exact power of two); else 0.5
   float div;           // SCALE_DIV: divisor d
   float rdiv;          // SCALE_DIV: RN(1/d)
+  unsigned stagger_ns; // start offset between the frame groups of a CTA (see the kernel)
 };
 
 template <int LOG2N_, int G_>
@@ -65,7 +71,14 @@ struct V2Cfg {
   // layout [0,32) window | [32,62) pass-2 twiddles | [64,94) last-pass twiddles | [96,112) recombination.
   // A thread's lane is 32*(warp%4)+lane_id; groups wider than 128 threads use T/128 column sets.
   static constexpr bool TMEM_TABLES = !FOUR;
-  static constexpr int TM_SETS = T > 128 ? T / 128 : 1, TM_SET_COLS = 128, TM_COLS = TM_SETS * TM_SET_COLS;
+  // Warp roles are rotated from group to group (thread 0 of a group does extra work -- the record, bin
+  // M/2 -- and would otherwise always sit on the same SM sub-partition): group g's logical warp w is
+  // physical warp (w - rot(g)) mod NW, rot(g) = (g / GPQ) % NROT.  One table copy per rotation.
+  static constexpr int NROT = T == 128 ? 4 : (T == 64 || T == 256) ? 2 : 1;
+  static constexpr int GPQ = T >= 128 ? 1 : 128 / T;          // groups per 4 physical warps
+  static constexpr int TM_JSETS = T > 128 ? T / 128 : 1;      // column sets needed to cover j >= 128
+  static constexpr int TM_SETS = TM_JSETS * NROT, TM_SET_COLS = 128, TM_COLS = TM_SETS * TM_SET_COLS;
+  static_assert(TM_COLS <= 512 && G_ / GPQ >= NROT, "TMEM table layout");
   static constexpr int TM_WIN = 0, TM_TW2 = 32, TM_TW3 = 64, TM_TWR = 96;
   static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2, NTW4 = FOUR ? (R4 - 1) * 4096 : 0;
   static constexpr int S_TW2 = TMEM_TABLES ? 0 : NTW2, S_TW3 = TMEM_TABLES ? 0 : NTW3;
@@ -81,7 +94,11 @@ struct V2Cfg {
   static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
   static constexpr size_t G_MISC = sizeof(uint32_t) * 96;
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
-  static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST;
+  // N = 2048..8192: the next frame's samples are staged in shared memory by a bulk asynchronous copy
+  // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
+  static constexpr bool TMA_STAGE = !FOUR && T >= 64;
+  static constexpr size_t G_STAGE = TMA_STAGE ? sizeof(float) * N + 16 : 0;   // samples + mbarrier
+  static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST + G_STAGE;
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
 };
 
@@ -153,14 +170,20 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
   const SpectrumParams &p = P.b;
   const int tid = threadIdx.x;
-  const int g = tid / T, j = tid - g * T;
-  const int lane = tid & 31, wig = j >> 5;  // warp index inside the group
+  const int g = tid / T;
+  const int rot = C::TMEM_TABLES ? (g / C::GPQ) % C::NROT : 0;
+  const int j = (tid - g * T + 32 * rot) & (T - 1);   // logical thread index inside the group
+  const int lane = tid & 31, wig = j >> 5;            // logical warp index inside the group
   unsigned char *gbase = smem + C::OFF_GROUPS + (size_t)g * C::G_BYTES;
   float2 *bufA = reinterpret_cast<float2 *>(gbase);
   float2 *bufB = reinterpret_cast<float2 *>(gbase + C::G_BUF);
   uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
   uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
   uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
+  unsigned char *stage = gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC + C::G_LIST;   // TMA_STAGE only
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + sizeof(float) * N);
+  constexpr bool TMA = C::TMA_STAGE;
+  uint32_t phase = 0;              // parity of the mbarrier phase the next wait completes
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
   constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
   uint32_t gw = 0u;                // 0: no guess yet (first frame of the group)
@@ -174,10 +197,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
   const int jbB = j ? 256 - j : 128;   // MIRROR: second last-pass butterfly of this thread
-  const uint32_t ta = tmem_addr(tm_base, tid >> 5, (j >> 7) * C::TM_SET_COLS);   // this thread's table row
+  const uint32_t ta = tmem_addr(tm_base, tid >> 5, (rot * C::TM_JSETS + (j >> 7)) * C::TM_SET_COLS);   // this thread's table row
   if constexpr (TM) {
-    // the first max(T,128) threads cover every (lane quadrant, column set) once
-    if (tid < (T > 128 ? T : 128)) {
+    // the first NROT * max(T,128) threads cover every (lane quadrant, column set) once
+    if (tid < C::NROT * (T > 128 ? T : 128)) {
       float v[16];
 #pragma unroll
       for (int h = 0; h < 2; h++) {   // window multipliers of samples 2n, 2n+1 for n = j + s*T
@@ -234,6 +257,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   auto twr_at = [&](int k) -> float2 { return __ldg(P.twr + k); };
   for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
   if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
+  if constexpr (TMA) {
+    if (j == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
+  }
   __syncthreads();
   if constexpr (TM) tmem_fence_after_sync();
 
@@ -246,16 +272,27 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   u64 frame = (u64)blockIdx.x * G + g;
   const u64 fstep = (u64)gridDim.x * G;
   if (frame >= p.n_frames) return;  // group-uniform; no CTA-wide barrier after this point
+  // Stagger the groups by a fraction of a frame time: groups in lockstep would all be in their
+  // shared-memory-heavy FFT phase (or all in their ALU/latency-heavy statistics phase) together.
+  if (G > 1 && g > 0) __nanosleep((unsigned)g * P.stagger_ns);
 
   // ---- load of the first frame (raw samples; the window is applied at the top of the loop) ------
   float2 x[E];
-  load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);   // pair-aligned (the host checks)
+  const uint32_t frame_bytes = (uint32_t)N * (p.in_i16 ? 2u : 4u);
+  // thread 0 of the group: bulk copy of frame f into the staging buffer (16-byte aligned, the host checks)
+  auto stage_frame = [&](u64 f) {
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(p.samples) + f * p.frame_stride * (p.in_i16 ? 2u : 4u);
+    mbar_arrive_expect_tx(mbar, frame_bytes);
+    bulk_copy_g2s(stage, src, frame_bytes, mbar);
+  };
+  if constexpr (TMA) { if (j == 0) stage_frame(frame); }
+  else load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);   // pair-aligned (the host checks)
   float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
 
   // thread 0: write the record fields of the previous frame (everything except a median written
   // by the "last pusher"), then reset the per-frame words.  Called right after a group barrier.
   auto flush_record = [&]() {
-    if (pend) {
+    if (pend && !(SA_EXP & 1)) {
       const bool mm = p.stats_mask & SA_STATS_MINMAX;
       uint4 r0;
       r0.x = mm ? __float_as_uint(v2_unkey<MODE>(pend_kmn)) : 0u;
@@ -277,6 +314,20 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
 #pragma unroll 1
   for (;;) {
+    const bool more = frame + fstep < p.n_frames;   // group-uniform
+    if constexpr (TMA) {
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+      if (p.in_i16) {
+        const short2 *src = reinterpret_cast<const short2 *>(stage);
+#pragma unroll
+        for (int s = 0; s < E; s++) { const short2 v = src[j + s * T]; x[s] = make_float2((float)v.x, (float)v.y); }
+      } else {
+        const float2 *src = reinterpret_cast<const float2 *>(stage);
+#pragma unroll
+        for (int s = 0; s < E; s++) x[s] = src[j + s * T];
+      }
+    }
 
     // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
     // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
@@ -306,7 +357,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       for (int k = 0; k < 16; k++) w[k] = x[k];
     }
     group_sync<T>(g);
-    if (want_stats && j == 0) flush_record();  // every thread of the group has finished the previous frame
+    // every thread of the group has consumed the staged samples and finished the previous frame
+    if constexpr (TMA) { if (j == 0 && more) stage_frame(frame + fstep); }
+    if (want_stats && j == 0) flush_record();
     {
       const float2 *r = wbuf + (j + (j >> 4));
 #pragma unroll
@@ -493,11 +546,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
     };
 
-    // ---- request the next frame now; its latency hides behind the statistics phase ---------------
     const u64 cur = frame;
     frame += fstep;
-    const bool more = frame < p.n_frames;
-    if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);
 
     // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
     uint32_t valid = 0xffffffffu;
@@ -577,7 +627,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
     // ---- statistics of the scaled values (src/spectrum.rs:481-539) --------------------------------
     if (want_stats) {
-      uint32_t *hist = hist0 + par * C::HSTRIDE;          // clean on entry
+      // layout of one histogram (HSTRIDE words): [3 pad | below | NBUCKET buckets (16-byte aligned) | above | pad]
+      uint32_t *hist_base = hist0 + par * C::HSTRIDE;     // clean on entry
+      uint32_t *hist = hist_base + 3;                     // hist[0] = below, hist[1 + b] = bucket b, hist[NBUCKET + 1] = above
       uint32_t *hist_other = hist0 + (par ^ 1) * C::HSTRIDE;  // possibly dirty from the previous frame
       par ^= 1;
       const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;   // middle ranks (0-based)
@@ -628,11 +680,15 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         if (valid_mid) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(vmid), winL, shw)], 1u);
       }
       const uint32_t my_kmn = kmn, my_kmx = kmx;
-      kmn = __reduce_min_sync(0xffffffffu, kmn);
-      kmx = __reduce_max_sync(0xffffffffu, kmx);
+      if (!(SA_EXP & 32)) {
+        kmn = __reduce_min_sync(0xffffffffu, kmn);
+        kmx = __reduce_max_sync(0xffffffffu, kmx);
+      }
+      if (!(SA_EXP & 8)) {
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-      if constexpr (NW > 1) {
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      }
+      if constexpr (NW > 1 && !(SA_EXP & 4)) {
         if (lane == 0) { misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum); }
         group_sync<T>(g);
         kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
@@ -646,7 +702,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         __syncwarp();
       }
       // arg bins: only threads that hold the extreme value search (min -> lowest bin, max -> highest)
-      if (my_kmn == kmn) {
+      if (my_kmn == kmn && !(SA_EXP & 2)) {
         uint32_t best = 0xffffffffu;
 #pragma unroll
         for (int i = 0; i < E; i++)
@@ -654,7 +710,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         if (valid_mid && v2_key<MODE>(vmid) == kmn) best = min(best, (uint32_t)(M / 2));
         atomicMin(&misc[MI_ARGMIN], best);
       }
-      if (my_kmx == kmx) {
+      if (my_kmx == kmx && !(SA_EXP & 2)) {
         uint32_t best = 0u;
 #pragma unroll
         for (int i = 0; i < E; i++)
@@ -700,34 +756,37 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         // ---- fast path: no further group barrier -------------------------------------------------
         // every warp scans the 256 buckets redundantly (8 per lane) and finds the bucket of the middle
         // rank; the histogram of the previous frame is cleared on the side
-        uint32_t hb[HBPL];
-        uint32_t local = 0;
-#pragma unroll
-        for (int b = 0; b < HBPL; b++) { hb[b] = hist[1 + lane * HBPL + b]; local += hb[b]; }
+        // two levels: 32 runs of 8 buckets (one per lane, two 16-byte loads), then the 8 buckets of the run
+        // that holds the rank
+        static_assert(HBPL == 8, "two-level scan assumes 8 buckets per lane");
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(hist + 1 + lane * 8);
+        const uint4 h1 = *reinterpret_cast<const uint4 *>(hist + 5 + lane * 8);
         const uint32_t nbelow = hist[0];
         for (int i = j; i < C::HSTRIDE; i += T) hist_other[i] = 0;
+        const uint32_t local = (h0.x + h0.y) + (h0.z + h0.w) + ((h1.x + h1.y) + (h1.z + h1.w));
         uint32_t incl = local;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
           const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
           if (lane >= off) incl += o;
         }
-        const uint32_t c0 = nbelow + incl - local;
-        const bool own = (ra >= c0) && (ra < c0 + local);
-        const uint32_t om = __ballot_sync(0xffffffffu, own);
-        uint32_t b_sel = 0, below = 0, cnt = 0;
-        if (own) {
-          uint32_t c = c0;
+        // first run whose inclusive count exceeds the rank (none: the window missed the middle rank)
+        uint32_t om = __ballot_sync(0xffffffffu, nbelow + incl > ra);
+        if (ra < nbelow) om = 0u;
+        const int owner = (__ffs(om) - 1) & 31;
+        const uint32_t c0o = nbelow + __shfl_sync(0xffffffffu, incl - local, owner);
+        const uint32_t h8 = hist[1 + owner * 8 + (lane & 7)];
+        uint32_t incl8 = h8;
 #pragma unroll
-          for (int b = 0; b < HBPL; b++) {
-            if (ra >= c && ra < c + hb[b]) { b_sel = lane * HBPL + b; below = c; cnt = hb[b]; }
-            c += hb[b];
-          }
+        for (int off = 1; off < 8; off <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl8, off, 8);
+          if ((lane & 7) >= off) incl8 += o;
         }
-        const int owner = __ffs(om) - 1;
-        const uint32_t ba = __shfl_sync(0xffffffffu, b_sel, owner & 31);
-        const uint32_t below_a = __shfl_sync(0xffffffffu, below, owner & 31);
-        const uint32_t cnt_a = __shfl_sync(0xffffffffu, cnt, owner & 31);
+        const uint32_t om8 = __ballot_sync(0xffffffffu, c0o + incl8 > ra) & 0xffu;
+        const int b8 = (__ffs(om8) - 1) & 7;
+        const uint32_t ba = (uint32_t)(owner * 8 + b8);
+        const uint32_t cnt_a = __shfl_sync(0xffffffffu, h8, b8);
+        const uint32_t below_a = c0o + __shfl_sync(0xffffffffu, incl8 - h8, b8);
         const uint32_t lo_a = winL + (ba << shw), bw = (1u << shw) - 1u;
         if (om != 0u && cnt_a <= 32u) {
           if (shw == 0) {
@@ -736,44 +795,39 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           } else {
             // candidates of the selected bucket go to the list; the thread that completes the list
             // ranks it and writes the median (and the next guess) -- nobody waits for it
-            uint32_t tmin = 0xffffffffu;
+            uint32_t npush = 0;
 #pragma unroll
-            for (int i = 0; i < E; i++)
-              if (SA_VALID(i)) tmin = min(tmin, v2_key<MODE>(val[i]) - lo_a);
-            if (valid_mid) tmin = min(tmin, v2_key<MODE>(vmid) - lo_a);
-            if (__any_sync(0xffffffffu, tmin <= bw)) {
-              if (tmin <= bw) {
-                uint32_t npush = 0;
-#pragma unroll
-                for (int i = 0; i < E; i++) {
-                  const uint32_t k = v2_key<MODE>(val[i]);
-                  if (SA_VALID(i) && (k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
-                }
-                if (valid_mid) {
-                  const uint32_t k = v2_key<MODE>(vmid);
-                  if ((k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
-                }
-                __threadfence_block();
-                const uint32_t done = atomicAdd(&misc[MI_LDONE], npush) + npush;
-                if (done == cnt_a) {
-                  __threadfence_block();
-                  const volatile uint32_t *vl = list;
-                  const uint32_t want = ra - below_a;
-                  uint32_t res = 0;
-                  for (uint32_t a = 0; a < cnt_a; a++) {
-                    const uint32_t kk = vl[a];
-                    uint32_t r = 0;
-                    for (uint32_t b = 0; b < cnt_a; b++) {
-                      const uint32_t ko = vl[b];
-                      r += (ko < kk || (ko == kk && b < a)) ? 1u : 0u;
-                    }
-                    if (r == want) res = kk;
-                  }
-                  reinterpret_cast<uint32_t *>(&p.stats[cur])[5] = __float_as_uint(v2_unkey<MODE>(res));
-                  misc[MI_GUESS] = res;
-                  misc[MI_LCOUNT] = 0u;
-                  misc[MI_LDONE] = 0u;
-                }
+            for (int i = 0; i < E; i++) {
+              const uint32_t k = v2_key<MODE>(val[i]);
+              if (SA_VALID(i) && (k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
+            }
+            if (valid_mid) {
+              const uint32_t k = v2_key<MODE>(vmid);
+              if ((k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
+            }
+            bool fin = false;
+            if (npush) {
+              __threadfence_block();
+              fin = (atomicAdd(&misc[MI_LDONE], npush) + npush == cnt_a);
+            }
+            // the warp of the thread that completed the list ranks it together: one candidate per lane,
+            // stable order (src/spectrum.rs:515-524 sorts, ties keep their order -- equal keys are equal values)
+            if (__any_sync(0xffffffffu, fin)) {
+              __threadfence_block();
+              const uint32_t mine = (lane < (int)cnt_a) ? reinterpret_cast<const volatile uint32_t *>(list)[lane] : 0xffffffffu;
+              uint32_t rank = 0;
+#pragma unroll 4
+              for (uint32_t c = 0; c < cnt_a; c++) {
+                const uint32_t o = __shfl_sync(0xffffffffu, mine, c);
+                rank += (o < mine || (o == mine && c < (uint32_t)lane)) ? 1u : 0u;
+              }
+              const uint32_t hit = __ballot_sync(0xffffffffu, lane < (int)cnt_a && rank == ra - below_a);
+              const uint32_t res = __shfl_sync(0xffffffffu, mine, (__ffs(hit) - 1) & 31);
+              if (lane == 0) {
+                reinterpret_cast<uint32_t *>(&p.stats[cur])[5] = __float_as_uint(v2_unkey<MODE>(res));
+                misc[MI_GUESS] = res;
+                misc[MI_LCOUNT] = 0u;
+                misc[MI_LDONE] = 0u;
               }
             }
             if (j == 0) pend_med = false;
@@ -783,7 +837,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         } else {
           // the guessed window missed the middle rank, or its bucket is crowded: exact loop below
           group_sync<T>(g);                                   // every warp has finished scanning
-          for (int i = j; i < C::HSTRIDE; i += T) hist[i] = 0;
+          for (int i = j; i < C::HSTRIDE; i += T) hist_base[i] = 0;
           group_sync<T>(g);
           need_slow = true;
           if (om == 0u) { win_failed = true; }
@@ -958,6 +1012,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
     }
 #undef SA_VALID
+    // without the staging buffer (N = 1024, 16384) the next frame is loaded after the statistics: issued
+    // before them, the loads share a register scoreboard with that phase and stall it instead of hiding
+    if constexpr (!TMA) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
     if (!more) break;
   }
   if (want_stats) {
