@@ -604,27 +604,6 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
     vmid = scale1(vmid);
 
-    // ---- store the surviving bins ------------------------------------------------------------------
-    {
-      float *dst = p.out_vals + cur * p.out_stride - lo;
-      if constexpr (MIRROR) {
-        // four address registers, compile-time offsets of +-256 q
-        float *d0 = dst + j, *d1 = dst + (M - j), *d2 = dst + jbB, *d3 = dst + (M - jbB);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          if (SA_VALID(4 * q)) d0[256 * q] = val[4 * q];
-          if (SA_VALID(4 * q + 1)) d1[-256 * q] = val[4 * q + 1];
-          if (SA_VALID(4 * q + 2)) d2[256 * q] = val[4 * q + 2];
-          if (SA_VALID(4 * q + 3)) d3[-256 * q] = val[4 * q + 3];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < E; i++)
-          if (SA_VALID(i)) dst[binof(i)] = val[i];
-      }
-      if (valid_mid) dst[M / 2] = vmid;
-    }
-
     // ---- statistics of the scaled values (src/spectrum.rs:481-539) --------------------------------
     if (want_stats) {
       // layout of one histogram (HSTRIDE words): [3 pad | below | NBUCKET buckets (16-byte aligned) | above | pad]
@@ -812,7 +791,26 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
             }
             // the warp of the thread that completed the list ranks it together: one candidate per lane,
             // stable order (src/spectrum.rs:515-524 sorts, ties keep their order -- equal keys are equal values)
-            if (__any_sync(0xffffffffu, fin)) {
+            if ((SA_EXP & 128) && fin) {   // experiment: the completing thread ranks the list alone
+              __threadfence_block();
+              const volatile uint32_t *vl = list;
+              const uint32_t want = ra - below_a;
+              uint32_t res = 0;
+              for (uint32_t a = 0; a < cnt_a; a++) {
+                const uint32_t kk = vl[a];
+                uint32_t r = 0;
+                for (uint32_t b = 0; b < cnt_a; b++) {
+                  const uint32_t ko = vl[b];
+                  r += (ko < kk || (ko == kk && b < a)) ? 1u : 0u;
+                }
+                if (r == want) res = kk;
+              }
+              reinterpret_cast<uint32_t *>(&p.stats[cur])[5] = __float_as_uint(v2_unkey<MODE>(res));
+              misc[MI_GUESS] = res;
+              misc[MI_LCOUNT] = 0u;
+              misc[MI_LDONE] = 0u;
+            }
+            if (!(SA_EXP & 128) && __any_sync(0xffffffffu, fin)) {
               __threadfence_block();
               const uint32_t mine = (lane < (int)cnt_a) ? reinterpret_cast<const volatile uint32_t *>(list)[lane] : 0xffffffffu;
               uint32_t rank = 0;
@@ -1011,6 +1009,28 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         }
       }
     }
+    // ---- store the surviving bins: after the statistics, whose dependent shuffle / shared-memory chains
+    // would otherwise queue behind 17 global stores per thread in the memory pipe -----------------------
+    {
+      float *dst = p.out_vals + cur * p.out_stride - lo;
+      if constexpr (MIRROR) {
+        // four address registers, compile-time offsets of +-256 q
+        float *d0 = dst + j, *d1 = dst + (M - j), *d2 = dst + jbB, *d3 = dst + (M - jbB);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (SA_VALID(4 * q)) d0[256 * q] = val[4 * q];
+          if (SA_VALID(4 * q + 1)) d1[-256 * q] = val[4 * q + 1];
+          if (SA_VALID(4 * q + 2)) d2[256 * q] = val[4 * q + 2];
+          if (SA_VALID(4 * q + 3)) d3[-256 * q] = val[4 * q + 3];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < E; i++)
+          if (SA_VALID(i)) dst[binof(i)] = val[i];
+      }
+      if (valid_mid) dst[M / 2] = vmid;
+    }
+
 #undef SA_VALID
     // without the staging buffer (N = 1024, 16384) the next frame is loaded after the statistics: issued
     // before them, the loads share a register scoreboard with that phase and stall it instead of hiding
