@@ -188,7 +188,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
   uint32_t gw = 0u;                // 0: no guess yet (first frame of the group)
   int par = 0;                     // which of the two histograms this frame uses
-  // record fields thread 0 writes one barrier later (after every thread finished the frame)
+  // record fields written one barrier later (after every thread finished the frame) by the first lane
+  // of the group's last warp; thread 0 already has bin M/2, the Nyquist bin and the bulk copies to do
+  const bool rec_thread = (j == T - 32);
   bool pend = false, pend_med = false;
   u64 pend_cur = 0;
   uint32_t pend_kmn = 0, pend_kmx = 0, pend_medkey = 0;
@@ -359,7 +361,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     group_sync<T>(g);
     // every thread of the group has consumed the staged samples and finished the previous frame
     if constexpr (TMA) { if (j == 0 && more) stage_frame(frame + fstep); }
-    if (want_stats && j == 0) flush_record();
+    if (want_stats && rec_thread) flush_record();
     {
       const float2 *r = wbuf + (j + (j >> 4));
 #pragma unroll
@@ -722,7 +724,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
       if (!want_median || (all_equal && !nonfinite)) {
         // nothing to select: thread 0 writes the whole record one barrier later
-        if (j == 0) {
+        if (rec_thread) {
           pend = true; pend_med = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; pend_medkey = kmn;
           if (want_median) misc[MI_GUESS] = kmn;
         }
@@ -770,19 +772,37 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         if (om != 0u && cnt_a <= 32u) {
           if (shw == 0) {
             // buckets are single keys: the median is lo_a itself; thread 0 writes it with the record
-            if (j == 0) { pend_med = true; pend_medkey = lo_a; misc[MI_GUESS] = lo_a; }
+            if (rec_thread) { pend_med = true; pend_medkey = lo_a; misc[MI_GUESS] = lo_a; }
           } else {
             // candidates of the selected bucket go to the list; the thread that completes the list
             // ranks it and writes the median (and the next guess) -- nobody waits for it
-            uint32_t npush = 0;
+            // branch-free count of this thread's candidates (plus the last one); almost always 0 or 1
+            uint32_t npush = 0, ck = 0;
 #pragma unroll
             for (int i = 0; i < E; i++) {
               const uint32_t k = v2_key<MODE>(val[i]);
-              if (SA_VALID(i) && (k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
+              const bool c = SA_VALID(i) && (k - lo_a) <= bw;
+              ck = c ? k : ck;
+              npush += c ? 1u : 0u;
             }
             if (valid_mid) {
               const uint32_t k = v2_key<MODE>(vmid);
-              if ((k - lo_a) <= bw) { list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k; npush++; }
+              const bool c = (k - lo_a) <= bw;
+              ck = c ? k : ck;
+              npush += c ? 1u : 0u;
+            }
+            if (npush == 1u) {
+              list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = ck;
+            } else if (npush > 1u) {
+#pragma unroll
+              for (int i = 0; i < E; i++) {   // rare: several candidates in one thread
+                const uint32_t k = v2_key<MODE>(val[i]);
+                if (SA_VALID(i) && (k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k;
+              }
+              if (valid_mid) {
+                const uint32_t k = v2_key<MODE>(vmid);
+                if ((k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k;
+              }
             }
             bool fin = false;
             if (npush) {
@@ -828,9 +848,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
                 misc[MI_LDONE] = 0u;
               }
             }
-            if (j == 0) pend_med = false;
+            if (rec_thread) pend_med = false;
           }
-          if (j == 0) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; }
+          if (rec_thread) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; }
           gw = max(gw - (gw >> 6), GW_MIN);
         } else {
           // the guessed window missed the middle rank, or its bucket is crowded: exact loop below
@@ -1039,7 +1059,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   }
   if (want_stats) {
     group_sync<T>(g);                 // every thread of the group has finished its last frame
-    if (j == 0) flush_record();
+    if (rec_thread) flush_record();
   }
 }
 
