@@ -358,14 +358,33 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
             if (split) { ka = ma; kb = mb; }
           }
           if (uselist) {
+            // branch-free count of this thread's candidates (plus the last one); almost always 0 or 1
+            uint32_t np = 0, ck = 0;
 #pragma unroll
             for (int i = 0; i < E; i++) {
               const uint32_t k = v2_key<MODE>(val[i]);
-              if (SA_VALID(i) && (k - lo_a) <= bw) list[atomicAdd(&misc[SM_LCOUNT], 1u) & 31u] = k;
+              const bool c = SA_VALID(i) && (k - lo_a) <= bw;
+              ck = c ? k : ck;
+              np += c ? 1u : 0u;
             }
             if (valid_mid) {
               const uint32_t k = v2_key<MODE>(vmid);
-              if ((k - lo_a) <= bw) list[atomicAdd(&misc[SM_LCOUNT], 1u) & 31u] = k;
+              const bool c = (k - lo_a) <= bw;
+              ck = c ? k : ck;
+              np += c ? 1u : 0u;
+            }
+            if (np == 1u) {
+              list[atomicAdd(&misc[SM_LCOUNT], 1u) & 31u] = ck;
+            } else if (np > 1u) {
+#pragma unroll
+              for (int i = 0; i < E; i++) {
+                const uint32_t k = v2_key<MODE>(val[i]);
+                if (SA_VALID(i) && (k - lo_a) <= bw) list[atomicAdd(&misc[SM_LCOUNT], 1u) & 31u] = k;
+              }
+              if (valid_mid) {
+                const uint32_t k = v2_key<MODE>(vmid);
+                if ((k - lo_a) <= bw) list[atomicAdd(&misc[SM_LCOUNT], 1u) & 31u] = k;
+              }
             }
           }
           __syncwarp();

@@ -550,6 +550,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
     const u64 cur = frame;
     frame += fstep;
+    // N = 16384 (one group per CTA, nothing else to overlap with): request the next frame before the statistics
+    if constexpr (C::FOUR) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
 
     // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
     uint32_t valid = 0xffffffffu;
@@ -1031,7 +1033,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
     // ---- store the surviving bins: after the statistics, whose dependent shuffle / shared-memory chains
     // would otherwise queue behind 17 global stores per thread in the memory pipe -----------------------
-    {
+    if (!(SA_EXP & 256)) {
       float *dst = p.out_vals + cur * p.out_stride - lo;
       if constexpr (MIRROR) {
         // four address registers, compile-time offsets of +-256 q
@@ -1052,9 +1054,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
 
 #undef SA_VALID
-    // without the staging buffer (N = 1024, 16384) the next frame is loaded after the statistics: issued
-    // before them, the loads share a register scoreboard with that phase and stall it instead of hiding
-    if constexpr (!TMA) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
+    // N = 1024 (no staging buffer, 16 one-warp groups per CTA) loads the next frame after the statistics:
+    // issued before them, the loads share a register scoreboard with that phase and stall it (measured)
+    if constexpr (!TMA && !C::FOUR) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
     if (!more) break;
   }
   if (want_stats) {
