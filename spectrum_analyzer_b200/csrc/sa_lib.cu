@@ -306,7 +306,7 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 11: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
     case 12: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
     case 13: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
-    case 14: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<14, 1>>(ctx, p);
+    case 14: return (ctx->use_generic || !p.aligned16) ? launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<14, 1>>(ctx, p);
     case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
     default: return SA_ERR_UNSUPPORTED_LENGTH;
   }

@@ -1,31 +1,43 @@
-// sa_spectrum_v2.cuh -- tuned fused kernel family for N in {1024, 2048, 4096, 8192} (T = N/32
+// sa_spectrum_v2.cuh -- tuned fused kernel family for N in {1024, 2048, 4096, 8192, 16384} (T = N/32
 // threads per frame, a multiple of the warp size).
 //
-// Same math and same outputs as sa_spectrum_kernel.cuh (the generic family), restructured around
-// what the v1 ncu profile showed (profiles/r01_v1_summary.md): the kernel is instruction- and
-// latency-bound, DRAM traffic already equals the algorithmic bytes.
+// Same math and same outputs as sa_spectrum_kernel.cuh (the generic family), restructured around what
+// the ncu profiles showed (profiles/README.md): DRAM traffic already equals the algorithmic bytes; the
+// kernel is bound by per-warp latency chains, the shared-memory/LSU pipe and instruction issue.
 //
 //  * CTA = G independent frame groups of T threads (G*T = 512): each group walks its own frames and
 //    synchronises with its own named barrier (bar.sync id, T), so groups overlap each other's
-//    barrier/latency phases; 16 warps/SM at <= 128 registers.
-//  * read-only tables live once per CTA in shared memory: window multipliers (src/windows.rs),
-//    per-pass twiddles laid out [k][p] (conflict-free / broadcast), recombination twiddles.
-//  * two exchange buffers per group, alternated on every exchange: one barrier per exchange.
-//  * next frame's samples are requested (ld.global.nc) right after the recombination, so their
-//    latency hides behind the statistics phase; the window multiply happens when they are consumed.
+//    barrier/latency phases; 16 warps/SM at <= 128 registers.  Warp roles rotate from group to group
+//    so that the extra work of a group's first and last warp is spread over the four SM sub-partitions.
+//  * per-thread constants (window multipliers src/windows.rs, pass twiddles, recombination twiddles:
+//    112 words per thread) live in TENSOR MEMORY and are read with tcgen05.ld (sa_tmem.cuh): TMEM has
+//    its own datapath, so a quarter of the former shared-memory traffic left the LSU pipe.
+//  * the next frame's samples are STAGED IN SHARED MEMORY BY A BULK ASYNCHRONOUS COPY (cp.async.bulk,
+//    one per frame, completion on an mbarrier) issued right after the first barrier of the current
+//    frame.  A register prefetch (ld.global ahead of the statistics) was slower than no prefetch at
+//    all: ptxas shares its six scoreboards between those loads and the LDS/SHFL/ATOMS of the statistics
+//    phase, which then waits for DRAM.  (N = 1024 has no room for the stage: it loads after the stats.)
+//  * two exchange buffers per group, alternated on every exchange: one barrier per exchange; N = 4096
+//    pairs the last-pass butterflies j and 256-j in one thread so the real-FFT recombination needs none.
 //  * magnitude = sqrt.approx(|.|^2) * c, where c folds the real-FFT 1/2 and a power-of-two scaling
 //    divisor (divide_by_N always, divide_by_N_sqrt when log2 N is even) into one exact multiply;
 //    other divisors use an exactly-rounded FMA division.
 //  * statistics: u32 min/max on the value bit patterns (3-input VIMNMX), redux.sync across the warp,
 //    arg-bins resolved only by the threads that hold the extreme value (stable-sort tie rules of
-//    src/spectrum.rs:496-499,529-530 via atomicMin / atomicMax on the bin index).
+//    src/spectrum.rs:496-499,529-530 via atomicMin / atomicMax on the bin index).  The record of a
+//    frame is written one barrier later by the group's last warp; the spectrum values are stored
+//    after the statistics so that their dependent SHFL/LDS chains do not queue behind 17 global
+//    stores per thread in the memory pipe.
 //  * NaN/Inf validation (src/lib.rs:168-173) costs nothing on clean frames: any non-finite input
 //    makes every output bin non-finite, so the maximum flags it and only then the group re-reads
 //    its samples to classify NaN vs Inf vs overflow.
-//  * median (src/spectrum.rs:515-524): exact selection by one histogram pass over up to 1024
-//    buckets spanning [min,max] of the value bit patterns, a block scan, compaction of the
-//    (typically < 8) candidates of the selected bucket and a warp-level rank count; degenerate
-//    distributions iterate the same pass on the narrowed range.
+//  * median (src/spectrum.rs:515-524): exact selection.  The keys are histogrammed (256 buckets +
+//    below/above, unconditional shared-memory atomics) against a window guessed from the previous
+//    frame's median, fused with the min/max/sum pass; after the one statistics barrier every warp
+//    scans the histogram (two levels, 16-byte loads), the (typically < 10) keys of the selected bucket
+//    are appended to a list, and the warp whose thread completes the list ranks it -- nobody waits.
+//    The ranks are verified against the counts; a missed window, an even count, a crowded bucket or a
+//    non-finite frame take the barrier-synchronised exact loop (full-range histogram, narrowing passes).
 #pragma once
 #include "sa_common.cuh"
 #include "sa_dft.cuh"
@@ -64,13 +76,11 @@ struct V2Cfg {
   static constexpr int BUF = M + M / 16;             // padded float2 elements of one exchange buffer
   static constexpr int HBITS = 8, NBUCKET = 1 << HBITS;   // median histogram: 256 buckets per pass
   static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
-  // big frames keep the window and the large twiddle tables in global memory (L1/L2, coalesced)
-  static constexpr bool GLOBAL_TABLES = FOUR;
-  // everything else keeps the per-thread constants (window multipliers, pass twiddles, recombination
+  // the per-thread constants (window multipliers, pass twiddles, recombination
   // twiddles: 112 words per thread) in tensor memory, read with tcgen05.ld (sa_tmem.cuh): column
   // layout [0,32) window | [32,62) pass-2 twiddles | [64,94) last-pass twiddles | [96,112) recombination.
   // A thread's lane is 32*(warp%4)+lane_id; groups wider than 128 threads use T/128 column sets.
-  static constexpr bool TMEM_TABLES = !FOUR;
+  // (the fourth-pass twiddles of N = 16384 stay in global memory)
   // Warp roles are rotated from group to group (thread 0 of a group does extra work -- the record, bin
   // M/2 -- and would otherwise always sit on the same SM sub-partition): group g's logical warp w is
   // physical warp (w - rot(g)) mod NW, rot(g) = (g / GPQ) % NROT.  One table copy per rotation.
@@ -81,14 +91,11 @@ struct V2Cfg {
   static_assert(TM_COLS <= 512 && G_ / GPQ >= NROT, "TMEM table layout");
   static constexpr int TM_WIN = 0, TM_TW2 = 32, TM_TW3 = 64, TM_TWR = 96;
   static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2, NTW4 = FOUR ? (R4 - 1) * 4096 : 0;
-  static constexpr int S_TW2 = TMEM_TABLES ? 0 : NTW2, S_TW3 = TMEM_TABLES ? 0 : NTW3;
   static_assert(T % 32 == 0 && T >= 32 && T <= 512, "v2 covers N = 1024..16384");
   static_assert(NT <= 1024 && (T == 32 || G_ <= 15), "named barriers 1..15");
   // shared memory map (bytes)
   static constexpr size_t OFF_TMSLOT = 0;                                  // TMEM base address (16 B slot)
-  static constexpr size_t OFF_TW2 = 16;
-  static constexpr size_t OFF_TW3 = OFF_TW2 + sizeof(float2) * S_TW2;
-  static constexpr size_t OFF_GROUPS = OFF_TW3 + sizeof(float2) * S_TW3;
+  static constexpr size_t OFF_GROUPS = 16;
   static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
   static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
   static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
@@ -96,7 +103,7 @@ struct V2Cfg {
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
   // N = 2048..8192: the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
-  static constexpr bool TMA_STAGE = !FOUR && T >= 64;
+  static constexpr bool TMA_STAGE = T >= 64;
   static constexpr size_t G_STAGE = TMA_STAGE ? sizeof(float) * N + 16 : 0;   // samples + mbarrier
   static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST + G_STAGE;
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
@@ -164,14 +171,11 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // outputs are exactly each other's mirror bins Z[k] <-> Z[M-k]: the real-FFT recombination then
   // needs no exchange and no barrier.
   constexpr bool MIRROR = (NB3 == 2);
-  constexpr bool TM = C::TMEM_TABLES;
-  float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);   // !TM only
-  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + C::OFF_TW3);   // !TM only
 
   const SpectrumParams &p = P.b;
   const int tid = threadIdx.x;
   const int g = tid / T;
-  const int rot = C::TMEM_TABLES ? (g / C::GPQ) % C::NROT : 0;
+  const int rot = (g / C::GPQ) % C::NROT;
   const int j = (tid - g * T + 32 * rot) & (T - 1);   // logical thread index inside the group
   const int lane = tid & 31, wig = j >> 5;            // logical warp index inside the group
   unsigned char *gbase = smem + C::OFF_GROUPS + (size_t)g * C::G_BYTES;
@@ -200,7 +204,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   const bool has_win = p.window != nullptr;
   const int jbB = j ? 256 - j : 128;   // MIRROR: second last-pass butterfly of this thread
   const uint32_t ta = tmem_addr(tm_base, tid >> 5, (rot * C::TM_JSETS + (j >> 7)) * C::TM_SET_COLS);   // this thread's table row
-  if constexpr (TM) {
+  {
     // the first NROT * max(T,128) threads cover every (lane quadrant, column set) once
     if (tid < C::NROT * (T > 128 ? T : 128)) {
       float v[16];
@@ -231,7 +235,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           float2 w = make_float2(0.f, 0.f);
           if (e < NB3 * (R3 - 1)) {
             const int b = e / (R3 - 1), k = e % (R3 - 1) + 1;
-            const int jb = MIRROR ? (b ? jbB : j) : j + b * T;
+            const int jb = MIRROR ? (b ? jbB : j) : C::FOUR ? (j & 255) : j + b * T;
             w = __ldg(P.tw3 + (k - 1) * 256 + jb);
           }
           v[2 * s] = w.x; v[2 * s + 1] = w.y;
@@ -247,23 +251,16 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       tmem_st16(ta + C::TM_TWR, v);
     }
     tmem_fence_before_sync();
-  } else {
-    for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
-    for (int i = tid; i < C::NTW3; i += C::NT) s_tw3[i] = __ldg(P.tw3 + i);
   }
-  // window multiplier pair / recombination twiddle from global memory (N = 16384, and the rare paths)
-  auto win2 = [&](int n) -> float2 {   // multipliers of samples 2n, 2n+1
-    return has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + n) : make_float2(1.f, 1.f);
-  };
+  // window multiplier from global memory (rare paths only)
   auto win1 = [&](int n) -> float { return has_win ? __ldg(p.window + n) : 1.0f; };
-  auto twr_at = [&](int k) -> float2 { return __ldg(P.twr + k); };
   for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
   if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
   if constexpr (TMA) {
     if (j == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
   }
   __syncthreads();
-  if constexpr (TM) tmem_fence_after_sync();
+  tmem_fence_after_sync();
 
   const uint32_t lo = p.bin_lo, hi = p.bin_hi;
   const uint32_t count = hi - lo + 1;
@@ -334,20 +331,13 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
     // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
     // skip the rounding of the windowed sample that the reference performs (src/windows.rs:47)
-    if constexpr (TM) {
+    {
       float w[32];
       tmem_ld32(ta + C::TM_WIN, w);
 #pragma unroll
       for (int s = 0; s < E; s++) {
         x[s].x = __fmul_rn(w[2 * s], x[s].x);
         x[s].y = __fmul_rn(w[2 * s + 1], x[s].y);
-      }
-    } else {
-#pragma unroll
-      for (int s = 0; s < E; s++) {
-        const float2 w = win2(j + s * T);
-        x[s].x = __fmul_rn(w.x, x[s].x);
-        x[s].y = __fmul_rn(w.y, x[s].y);
       }
     }
 
@@ -370,15 +360,11 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     { float2 *t = wbuf; wbuf = obuf; obuf = t; }
 
     // ---- pass 2: radix 16, NS = 16 ---------------------------------------------------------------
-    if constexpr (TM) {
+    {
       float t[32];
       tmem_ld32(ta + C::TM_TW2, t);
 #pragma unroll
       for (int k = 1; k < 16; k++) x[k] = cmul(x[k], make_float2(t[2 * (k - 1)], t[2 * (k - 1) + 1]));
-    } else {
-      const int pp = j & 15;
-#pragma unroll
-      for (int k = 1; k < 16; k++) x[k] = cmul(x[k], s_tw2[(k - 1) * 16 + pp]);
     }
     dft16(x);
     {
@@ -448,9 +434,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       if constexpr (C::FOUR) {
         // ---- pass 3: radix 16, NS = 256 (one butterfly per thread) ---------------------------------
         {
-          const int p3 = j & 255;
+          float t[32];
+          tmem_ld32(ta + C::TM_TW3, t);     // w_4096^(k (j mod 256)), k = 1..15
 #pragma unroll
-          for (int k = 1; k < 16; k++) x[k] = cmul(x[k], s_tw3[(k - 1) * 256 + p3]);
+          for (int k = 1; k < 16; k++) x[k] = cmul(x[k], make_float2(t[2 * (k - 1)], t[2 * (k - 1) + 1]));
         }
         dft16(x);
         {
@@ -511,12 +498,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
         const float2 *r = wbuf + (M / 2 - j);
         float tr[16];
-        if constexpr (TM) tmem_ld16(ta + C::TM_TWR, tr);
+        tmem_ld16(ta + C::TM_TWR, tr);
 #pragma unroll
         for (int s = 0; s < E / 2; s++) {
           const float2 a = x[s];
           const float2 bq = r[-s * T];
-          const float2 w = TM ? make_float2(tr[2 * s], tr[2 * s + 1]) : twr_at(j + s * T);
+          const float2 w = make_float2(tr[2 * s], tr[2 * s + 1]);
           // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
           const float2 cb = make_float2(bq.x, -bq.y);
           const float2 pp = add2(a, cb), qq = sub2(a, cb);
@@ -550,8 +537,6 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
     const u64 cur = frame;
     frame += fstep;
-    // N = 16384 (one group per CTA, nothing else to overlap with): request the next frame before the statistics
-    if constexpr (C::FOUR) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
 
     // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
     uint32_t valid = 0xffffffffu;
@@ -1056,7 +1041,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #undef SA_VALID
     // N = 1024 (no staging buffer, 16 one-warp groups per CTA) loads the next frame after the statistics:
     // issued before them, the loads share a register scoreboard with that phase and stall it (measured)
-    if constexpr (!TMA && !C::FOUR) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
+    if constexpr (!TMA) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
     if (!more) break;
   }
   if (want_stats) {
@@ -1068,22 +1053,18 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 template <class C, int MODE, bool FULL>
 __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t tm_base = 0;
-  if constexpr (C::TMEM_TABLES) {
-    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + C::OFF_TMSLOT);
-    if (threadIdx.x < 32) tmem_alloc<C::TM_COLS>(slot);
-    tmem_fence_before_sync();
-    __syncthreads();
-    tmem_fence_after_sync();
-    tm_base = *slot;
-  }
+  // tensor-memory allocation for the per-thread tables (one warp allocates, everybody reads the address)
+  uint32_t *slot = reinterpret_cast<uint32_t *>(smem + C::OFF_TMSLOT);
+  if (threadIdx.x < 32) tmem_alloc<C::TM_COLS>(slot);
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  const uint32_t tm_base = *slot;
   spectrum_body_v2<C, MODE, FULL>(P, smem, tm_base);
-  if constexpr (C::TMEM_TABLES) {
-    // groups finish at different times: the allocation is released once every thread is done with it
-    tmem_fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc<C::TM_COLS>(tm_base);
-  }
+  // groups finish at different times: the allocation is released once every thread is done with it
+  tmem_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<C::TM_COLS>(tm_base);
 }
 
 }  // namespace sa
