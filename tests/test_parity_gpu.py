@@ -311,3 +311,32 @@ def test_int16_ingestion_equals_f32_path(gpu_ctx, n, hop, offset):
     assert code == 0 and np.all(ostatus == 0)
     gv = got.vals.cpu().numpy()[:, : got.n_bins]
     assert np.all(np.abs(gv - ov) <= MAG_RTOL * ov.max(axis=1, keepdims=True))
+
+
+@pytest.mark.parametrize("n,counts", [(2048, [1, 7, 8, 9, 1183, 1184, 1185]), (4096, [1, 3, 4, 5, 591, 592, 593, 1185]),
+                                      (8192, [1, 2, 3, 295, 296, 297]), (16384, [1, 2, 147, 148, 149, 300])])
+def test_frame_counts_around_grid_boundaries(gpu_ctx, n, counts):
+    """The tuned kernels are persistent (one CTA per SM, G frame groups per CTA, frames dealt round-robin):
+    frame counts below / at / just above G and 148*G must give, frame for frame, the very bits of a longer run
+    (every frame is a pure function of its own samples, src/lib.rs:157-337; the median is exact whatever window
+    the group guessed from its previous frame)."""
+    import torch
+    m = sa()
+    total = max(counts)
+    x = torch.from_numpy(noise(total, n, seed=7 * n)).cuda()
+    kw = dict(window=O.WINDOW_HANN, n=n, frame_stride=n, stats=7)
+    ref = m.samples_fft_to_spectrum_batched(x, 44100, m.FrequencyLimit.All, m.scaling.divide_by_N_sqrt, n_frames=total, **kw)
+    torch.cuda.synchronize()
+    rv, rs = ref.vals.cpu().numpy().view(np.uint32), ref.stats_numpy()
+    assert np.all(rs["status"] == 0)
+    for f in counts:
+        got = m.samples_fft_to_spectrum_batched(x, 44100, m.FrequencyLimit.All, m.scaling.divide_by_N_sqrt, n_frames=f, **kw)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.vals.cpu().numpy().view(np.uint32), rv[:f]), f"values differ at n_frames={f}"
+        assert got.stats_numpy().tobytes() == rs[:f].tobytes(), f"stats differ at n_frames={f}"
+    # and the long run itself against the oracle on its last frames (the ones dealt last)
+    code, ov, _, ostatus, _ = O.spectrum_batched(x.cpu().numpy()[(total - 4) * n:], 4, n, n, 44100, O.LIMIT_ALL, 0.0, 0.0,
+                                                 O.WINDOW_HANN, O.SCALING_DIVIDE_BY_N_SQRT)
+    assert code == 0 and np.all(ostatus == 0)
+    gv = ref.vals.cpu().numpy()[total - 4:, : ref.n_bins]
+    assert np.all(np.abs(gv - ov) <= MAG_RTOL * ov.max(axis=1, keepdims=True))
