@@ -206,6 +206,12 @@ int sa_apply_scaling_chain_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames
                                    uint64_t stride, uint32_t bin_lo, uint32_t n, const int *scaling_kinds,
                                    uint32_t n_kinds, uint32_t stats_mask, sa_frame_stats *d_stats);
 
+/* The same on HOST buffers (in place; one spectrum or a batch): what `FrequencySpectrum::apply_scaling_fn`
+ * (src/spectrum.rs:128-168) of a host-side spectrum object calls.  Synchronous. */
+int sa_apply_scaling_chain_host(sa_ctx *ctx, float *h_vals, uint64_t n_frames, uint32_t n_bins,
+                                uint64_t stride, uint32_t bin_lo, uint32_t n, const int *scaling_kinds,
+                                uint32_t n_kinds, uint32_t stats_mask, sa_frame_stats *h_stats);
+
 /* windows::*_window on a device-resident batch: d_out[f*n + i] = w_i * d_in[f*frame_stride + i]. */
 int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t n_frames, uint32_t n,
                       uint64_t frame_stride, float *d_out);

@@ -67,6 +67,9 @@ extern "C" {
     pub fn sa_apply_scaling_chain_batched(ctx: *mut sa_ctx, d_vals: *mut f32, n_frames: u64, n_bins: u32, stride: u64,
                                           bin_lo: u32, n: u32, scaling_kinds: *const c_int, n_kinds: u32,
                                           stats_mask: u32, d_stats: *mut sa_frame_stats) -> c_int;
+    pub fn sa_apply_scaling_chain_host(ctx: *mut sa_ctx, h_vals: *mut f32, n_frames: u64, n_bins: u32, stride: u64,
+                                          bin_lo: u32, n: u32, scaling_kinds: *const c_int, n_kinds: u32,
+                                          stats_mask: u32, h_stats: *mut sa_frame_stats) -> c_int;
     pub fn sa_window_batched(ctx: *mut sa_ctx, window_kind: c_int, d_in: *const f32, n_frames: u64, n: u32,
                              frame_stride: u64, d_out: *mut f32) -> c_int;
     pub fn sa_window_host(ctx: *mut sa_ctx, window_kind: c_int, h_in: *const f32, n_frames: u64, n: u32,

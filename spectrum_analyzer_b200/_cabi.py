@@ -71,6 +71,7 @@ SYMBOLS = {
     "sa_spectrum_single": (_i, [_vp, _vp, _u64, _u32, _i, _f, _f, _i, _i, _vp, _vp, _u32p, _vp]),
     "sa_apply_scaling_batched": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _u32, _i, _u32, _vp]),
     "sa_apply_scaling_chain_batched": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _u32, _vp, _u32, _u32, _vp]),
+    "sa_apply_scaling_chain_host": (_i, [_vp, _vp, _u64, _u32, _u64, _u32, _u32, _vp, _u32, _u32, _vp]),
     "sa_window_batched": (_i, [_vp, _i, _vp, _u64, _u32, _u64, _vp]),
     "sa_window_host": (_i, [_vp, _i, _vp, _u64, _u32, _u64, _vp]),
     "sa_generate_noise": (_i, [_vp, _vp, _u64, _u64, _u64]),

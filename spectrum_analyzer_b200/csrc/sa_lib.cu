@@ -722,6 +722,34 @@ int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint
                                         d_stats);
 }
 
+int sa_apply_scaling_chain_host(sa_ctx *ctx, float *h_vals, uint64_t n_frames, uint32_t n_bins, uint64_t stride,
+                                uint32_t bin_lo, uint32_t n, const int *scaling_kinds, uint32_t n_kinds,
+                                uint32_t stats_mask, sa_frame_stats *h_stats) {
+  if (!ctx || !h_vals || !h_stats || n_bins < 2 || stride < n_bins || n < 2) return SA_ERR_INVALID_ARGUMENT;
+  if (n_frames == 0) return SA_OK;
+  SA_CUDA(cudaSetDevice(ctx->device));
+  const uint64_t cf = std::min<uint64_t>(n_frames, std::max<uint64_t>(1, (64ull << 20) / (stride * sizeof(float))));
+  int pe = ensure_pipeline(ctx, cf * stride * sizeof(float), 16, cf * sizeof(sa_frame_stats));
+  if (pe != SA_OK) return pe;
+  for (uint64_t f0 = 0; f0 < n_frames; f0 += cf) {   // simple serial chunks: this is not the hot entry point
+    const uint64_t nf = std::min(cf, n_frames - f0);
+    float *d_vals = static_cast<float *>(ctx->slot_in[0]);
+    SA_CUDA(cudaMemcpyAsync(d_vals, h_vals + f0 * stride, ((nf - 1) * stride + n_bins) * sizeof(float),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    SA_CUDA(cudaMemcpyAsync(ctx->slot_stats[0], h_stats + f0, nf * sizeof(sa_frame_stats), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    pe = sa_apply_scaling_chain_batched(ctx, d_vals, nf, n_bins, stride, bin_lo, n, scaling_kinds, n_kinds, stats_mask,
+                                        ctx->slot_stats[0]);
+    if (pe != SA_OK) return pe;
+    SA_CUDA(cudaMemcpyAsync(h_vals + f0 * stride, d_vals, ((nf - 1) * stride + n_bins) * sizeof(float),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(cudaMemcpyAsync(h_stats + f0, ctx->slot_stats[0], nf * sizeof(sa_frame_stats), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SA_OK;
+}
+
 int sa_window_batched(sa_ctx *ctx, int window_kind, const float *d_in, uint64_t n_frames, uint32_t n,
                       uint64_t frame_stride, float *d_out) {
   if (!ctx || !d_in || !d_out || n == 0 || n > 32768) return SA_ERR_INVALID_ARGUMENT;

@@ -96,6 +96,75 @@ int main() {
                                              &scaling::divide_by_N_sqrt, SA_WINDOW_HAMMING).unwrap();
     CHECK(b.n_bins == 1025 && b.vals.size() == 64 * 1025 && b.frequencies[1024] == 22050.0f);
     for (auto &st : b.stats) CHECK(st.status == SA_OK && st.min_val <= st.median && st.median <= st.max_val);
+    // the same frames as int16 PCM (src/tests/mod.rs:70-73 converts on the caller's side): identical bits
+    std::vector<int16_t> pcm(x.size());
+    std::vector<float> xf(x.size());
+    for (size_t i = 0; i < x.size(); i++) { pcm[i] = (int16_t)(x[i] * 20000.0f); xf[i] = (float)pcm[i]; }
+    auto bf = samples_fft_to_spectrum_batched(ctx, xf.data(), 64, 2048, 2048, 44100, FrequencyLimit::All(),
+                                              &scaling::divide_by_N_sqrt, SA_WINDOW_HAMMING).unwrap();
+    auto bi = samples_fft_to_spectrum_batched(ctx, pcm.data(), 64, 2048, 2048, 44100, FrequencyLimit::All(),
+                                              &scaling::divide_by_N_sqrt, SA_WINDOW_HAMMING).unwrap();
+    CHECK(bf.vals == bi.vals);
+    for (size_t f = 0; f < 64; f++) CHECK(bf.stats[f].median == bi.stats[f].median && bf.stats[f].max_bin == bi.stats[f].max_bin);
+  }
+  {  // src/spectrum.rs:656-792 test_spectrum_basic: lookups on a hand-made spectrum (host-side, known answers)
+    std::vector<FrequencySpectrum::Pair> v = {{0.f, 5.f},    {50.f, 50.f},  {100.f, 100.f}, {150.f, 150.f}, {200.f, 100.f},
+                                              {250.f, 20.f}, {300.f, 0.f},  {450.f, 200.f}, {500.f, 100.f}};
+    sa_frame_stats st{};
+    st.min_val = 0.f; st.min_bin = 6; st.max_val = 200.f; st.max_bin = 7; st.average = 80.55556f; st.median = 100.f;
+    FrequencySpectrum s(v, 50.0f, (uint32_t)v.size(), st, 0);
+    float dc = -1.f;
+    CHECK(s.dc_component(&dc) && dc == 5.0f);
+    CHECK(s.min() == FrequencySpectrum::Pair(300.f, 0.f) && s.max() == FrequencySpectrum::Pair(450.f, 200.f));
+    CHECK(s.range() == 200.f && s.min_fr() == 0.f && s.max_fr() == 500.f && s.frequency_resolution() == 50.f);
+    const float fx[8] = {0.f, 50.f, 150.f, 200.f, 250.f, 300.f, 375.f, 450.f};
+    const float fy[8] = {5.f, 50.f, 150.f, 100.f, 20.f, 0.f, 100.f, 200.f};
+    for (int i = 0; i < 8; i++) CHECK(s.freq_val_exact(fx[i]) == fy[i]);
+    CHECK(s.freq_val_closest(0.f) == FrequencySpectrum::Pair(0.f, 5.f));
+    CHECK(s.freq_val_closest(50.f) == FrequencySpectrum::Pair(50.f, 50.f));
+    CHECK(s.freq_val_closest(450.f) == FrequencySpectrum::Pair(450.f, 200.f));
+    CHECK(s.freq_val_closest(448.f) == FrequencySpectrum::Pair(450.f, 200.f));
+    CHECK(s.freq_val_closest(400.f) == FrequencySpectrum::Pair(450.f, 200.f));
+    CHECK(s.freq_val_closest(47.3f) == FrequencySpectrum::Pair(50.f, 50.f));
+    CHECK(s.freq_val_closest(51.3f) == FrequencySpectrum::Pair(50.f, 50.f));
+    // src/spectrum.rs:795-867: out-of-range lookups panic in the reference -> std::out_of_range here
+    int thrown = 0;
+    for (float bad : {-1.0f, 501.0f}) {
+      try { (void)s.freq_val_exact(bad); } catch (const std::out_of_range &) { thrown++; }
+      try { (void)s.freq_val_closest(bad); } catch (const std::out_of_range &) { thrown++; }
+    }
+    CHECK(thrown == 4);
+    // src/spectrum.rs:984-997 test_mel_getter: 450 mel = 343.6 Hz is inside, 4500 mel is far outside
+    std::vector<FrequencySpectrum::Pair> two = {{0.f, 5.f}, {450.f, 200.f}};
+    FrequencySpectrum t(two, 50.0f, 2, st, 0);
+    CHECK(std::fabs(FrequencySpectrum::mel_to_hertz(450.f) - 343.6f) < 0.5f);
+    thrown = 0;
+    try { (void)t.mel_val(4500.f); } catch (const std::out_of_range &) { thrown++; }
+    CHECK(thrown == 1);
+    CHECK(std::fabs(FrequencySpectrum::hertz_to_mel(FrequencySpectrum::mel_to_hertz(1000.f)) - 1000.f) < 1e-2f);
+    auto m = s.to_map();
+    CHECK(m.size() == 9 && m.at(450) == 200.f && m.at(0) == 5.f);
+    CHECK(s.to_mel_map().size() == 9);
+  }
+  {  // FrequencySpectrum::apply_scaling_fn (src/spectrum.rs:128-168) and scaling::combined (src/scaling.rs:174-182):
+     // scaling after the fact == scaling in the call, bit for bit, and the statistics are recalculated
+    auto audio = sine_wave_audio_data_multiple({50.0f, 1000.0f, 3777.0f}, 44100, 1000);
+    std::vector<float> frame(audio.begin(), audio.begin() + 2048);
+    auto plain = samples_fft_to_spectrum(ctx, frame, 44100, FrequencyLimit::Max(4000.0f), nullptr, SA_WINDOW_HANN).unwrap();
+    auto direct = samples_fft_to_spectrum(ctx, frame, 44100, FrequencyLimit::Max(4000.0f), &scaling::divide_by_N_sqrt,
+                                          SA_WINDOW_HANN).unwrap();
+    CHECK(plain.apply_scaling_fn(ctx, scaling::divide_by_N_sqrt).is_ok());
+    CHECK(plain.data().size() == direct.data().size());
+    for (size_t i = 0; i < plain.data().size(); i++) CHECK(plain.data()[i].second == direct.data()[i].second);
+    CHECK(plain.max() == direct.max() && plain.min() == direct.min() && plain.median() == direct.median());
+    // combined(divide_by_N, zero_to_one): both steps see the statistics from before the call
+    auto a = samples_fft_to_spectrum(ctx, frame, 44100, FrequencyLimit::Max(4000.0f), nullptr, SA_WINDOW_HANN).unwrap();
+    const float old_max = a.max().second;
+    std::vector<float> before;
+    for (auto &p : a.data()) before.push_back(p.second);
+    CHECK(a.apply_scaling_fn(ctx, scaling::combined({scaling::divide_by_N, scaling::scale_to_zero_to_one})).is_ok());
+    for (size_t i = 0; i < before.size(); i++) CHECK(a.data()[i].second == (before[i] / 2048.0f) / old_max);
+    CHECK(a.max().second == (old_max / 2048.0f) / old_max);
   }
   std::printf("reference_suite OK: %d checks\n", g_checks);
   return 0;
