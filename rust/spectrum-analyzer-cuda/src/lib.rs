@@ -136,6 +136,22 @@ impl FrequencySpectrum {
     pub fn max_fr(&self) -> f32 { self.data[self.data.len() - 1].0 }
     pub fn min_fr(&self) -> f32 { self.data[0].0 }
     pub fn dc_component(&self) -> Option<f32> { if self.data[0].0 == 0.0 { Some(self.data[0].1) } else { None } }
+
+    /// `apply_scaling_fn` (reference src/spectrum.rs:128-168) for a chain of built-in functions
+    /// (`scaling::combined`, src/scaling.rs:174-182: every function sees the statistics from before the call);
+    /// computed on the device, statistics recalculated.
+    pub fn apply_scaling_fn(&mut self, ctx: &Context, chain: &[ScalingFn]) -> Result<(), SpectrumAnalyzerError> {
+        let kinds: Vec<c_int> = chain.iter().map(|s| *s as c_int).collect();
+        let mut vals: Vec<f32> = self.data.iter().map(|p| p.1).collect();
+        let e = unsafe {
+            ffi::sa_apply_scaling_chain_host(ctx.raw, vals.as_mut_ptr(), 1, vals.len() as u32, vals.len() as u64,
+                                             self.bin_lo, self.samples_len, kinds.as_ptr(), kinds.len() as u32,
+                                             ffi::SA_STATS_ALL, &mut self.stats)
+        };
+        if e != ffi::SA_OK { return Err(map_err(e, FrequencyLimit::All)); }
+        for (p, v) in self.data.iter_mut().zip(vals) { p.1 = v; }
+        Ok(())
+    }
 }
 
 /// Drop-in for `samples_fft_to_spectrum` (reference src/lib.rs:157-162); `ctx` is the only extra argument.
@@ -188,6 +204,32 @@ pub fn samples_fft_to_spectrum_batched(ctx: &Context, frames: &[f32], n: u32, fr
                                       window as c_int, scaling_fn.map_or(0, |s| s as c_int), ffi::SA_STATS_ALL,
                                       out.vals.as_mut_ptr(), n_bins as u64, out.stats.as_mut_ptr(),
                                       ptr::null_mut(), ptr::null_mut())
+    };
+    if e != ffi::SA_OK { return Err(map_err(e, frequency_limit)); }
+    Ok(out)
+}
+
+/// The batched entry point on int16 PCM: replaces the caller-side `samples.iter().map(|x| *x as f32)` of the
+/// reference's tests and examples (src/tests/mod.rs:70-73); the conversion happens while the kernel loads.
+#[allow(clippy::too_many_arguments)]
+pub fn samples_fft_to_spectrum_batched_i16(ctx: &Context, frames: &[i16], n: u32, frame_stride: u64, n_frames: u64,
+                                           sampling_rate: u32, frequency_limit: FrequencyLimit,
+                                           scaling_fn: Option<ScalingFn>, window: windows::Window)
+                                           -> Result<BatchedSpectrum, SpectrumAnalyzerError> {
+    let (lk, lo, hi) = frequency_limit.raw();
+    let (mut bin_lo, mut n_bins) = (0u32, 0u32);
+    let e = unsafe { ffi::sa_limit_to_bins(n, sampling_rate, lk, lo, hi, &mut bin_lo, &mut n_bins) };
+    if e != ffi::SA_OK { return Err(map_err(e, frequency_limit)); }
+    assert!(n_frames == 0 || frames.len() as u64 >= (n_frames - 1) * frame_stride + n as u64);
+    let mut out = BatchedSpectrum { vals: vec![0.0; (n_frames * n_bins as u64) as usize],
+                                    stats: vec![ffi::sa_frame_stats::default(); n_frames as usize],
+                                    frequencies: vec![0.0; n_bins as usize], bin_lo, n_bins };
+    unsafe { ffi::sa_bin_frequencies(n, sampling_rate, bin_lo, n_bins, out.frequencies.as_mut_ptr()); }
+    let e = unsafe {
+        ffi::sa_spectrum_batched_host_i16(ctx.raw, frames.as_ptr(), n_frames, n, frame_stride, sampling_rate, lk, lo, hi,
+                                          window as c_int, scaling_fn.map_or(0, |s| s as c_int), ffi::SA_STATS_ALL,
+                                          out.vals.as_mut_ptr(), n_bins as u64, out.stats.as_mut_ptr(),
+                                          ptr::null_mut(), ptr::null_mut())
     };
     if e != ffi::SA_OK { return Err(map_err(e, frequency_limit)); }
     Ok(out)
