@@ -47,6 +47,7 @@ def main():
         ("64 hann all none", 64, 64, 32 * 1024 * 1024, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
         ("512 hann all none", 512, 512, 8 * 1024 * 1024, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
         ("32768 hann all none", 32768, 32768, 65_536, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
+        ("2048 hamming hop441 (odd hop: frames on 4-byte boundaries)", 2048, 441, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
         ("i16 cfg2 4096 hann all div_sqrt", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All, cabi.SCALING_DIVIDE_BY_N_SQRT, 7),
         ("i16 cfg3 2048 hamming hop512", 2048, 512, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
     ]

@@ -25,7 +25,7 @@ struct SpectrumParams {
   float scale_div;            // stats.n (divide_by_N) or sqrtf(stats.n) (divide_by_N_sqrt)
   int aligned8;               // samples base and frame_stride allow pair loads (8 B for f32, 4 B for i16)
   int in_i16;                 // samples are int16 PCM (converted exactly, `x as f32`, when loaded)
-  int aligned16;              // every frame starts on a 16-byte boundary (bulk copies into shared memory)
+  int aligned16;              // every frame starts on a 16-byte boundary (fast path of the staged loads)
 };
 
 // ---- sample loads: f32, or int16 PCM converted on the fly (the reference's callers do `x as f32`,

@@ -104,7 +104,7 @@ struct V2Cfg {
   // N = 2048..8192: the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
   static constexpr bool TMA_STAGE = T >= 64;
-  static constexpr size_t G_STAGE = TMA_STAGE ? sizeof(float) * N + 16 : 0;   // samples + mbarrier
+  static constexpr size_t G_STAGE = TMA_STAGE ? sizeof(float) * N + 32 : 0;   // samples (+16 B of alignment slack) + mbarrier
   static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST + G_STAGE;
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
 };
@@ -185,7 +185,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
   uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
   unsigned char *stage = gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC + C::G_LIST;   // TMA_STAGE only
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + sizeof(float) * N);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + sizeof(float) * N + 16);
   constexpr bool TMA = C::TMA_STAGE;
   uint32_t phase = 0;              // parity of the mbarrier phase the next wait completes
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
@@ -277,15 +277,28 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
   // ---- load of the first frame (raw samples; the window is applied at the top of the loop) ------
   float2 x[E];
-  const uint32_t frame_bytes = (uint32_t)N * (p.in_i16 ? 2u : 4u);
-  // thread 0 of the group: bulk copy of frame f into the staging buffer (16-byte aligned, the host checks)
+  // Byte address of frame f.  Bulk copies need 16-byte aligned addresses and sizes: the copy fetches the
+  // aligned superset [addr & ~15, round_up_16(addr + frame bytes)) and the frame sits `addr & 15` bytes into
+  // the staging buffer.  (The superset stays inside the 256-byte granules CUDA allocations are made of.)
+  const uint32_t esz = p.in_i16 ? 2u : 4u;
+  const uintptr_t base_addr = reinterpret_cast<uintptr_t>(p.samples);
+  auto frame_addr = [&](u64 f) -> uintptr_t { return base_addr + f * p.frame_stride * esz; };
+  // thread 0 of the group: bulk copy of frame f into the staging buffer
+  const bool al16 = p.aligned16 != 0;   // launch-uniform: every frame starts on a 16-byte boundary
   auto stage_frame = [&](u64 f) {
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(p.samples) + f * p.frame_stride * (p.in_i16 ? 2u : 4u);
-    mbar_arrive_expect_tx(mbar, frame_bytes);
-    bulk_copy_g2s(stage, src, frame_bytes, mbar);
+    const uintptr_t a = frame_addr(f);
+    if (al16) {
+      mbar_arrive_expect_tx(mbar, (uint32_t)N * esz);
+      bulk_copy_g2s(stage, reinterpret_cast<const void *>(a), (uint32_t)N * esz, mbar);
+    } else {
+      const uintptr_t a0 = a & ~(uintptr_t)15;
+      const uint32_t bytes = (uint32_t)(((a - a0) + (uintptr_t)N * esz + 15u) & ~(uintptr_t)15);
+      mbar_arrive_expect_tx(mbar, bytes);
+      bulk_copy_g2s(stage, reinterpret_cast<const void *>(a0), bytes, mbar);
+    }
   };
   if constexpr (TMA) { if (j == 0) stage_frame(frame); }
-  else load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);   // pair-aligned (the host checks)
+  else load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);   // N = 1024: pair-aligned (the host checks)
   float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
 
   // thread 0: write the record fields of the previous frame (everything except a median written
@@ -317,14 +330,29 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     if constexpr (TMA) {
       mbar_wait(mbar, phase);
       phase ^= 1u;
-      if (p.in_i16) {
-        const short2 *src = reinterpret_cast<const short2 *>(stage);
+      if (al16) {
+        if (p.in_i16) {
+          const short2 *src = reinterpret_cast<const short2 *>(stage);
 #pragma unroll
-        for (int s = 0; s < E; s++) { const short2 v = src[j + s * T]; x[s] = make_float2((float)v.x, (float)v.y); }
+          for (int s = 0; s < E; s++) { const short2 v = src[j + s * T]; x[s] = make_float2((float)v.x, (float)v.y); }
+        } else {
+          const float2 *src = reinterpret_cast<const float2 *>(stage);
+#pragma unroll
+          for (int s = 0; s < E; s++) x[s] = src[j + s * T];
+        }
       } else {
-        const float2 *src = reinterpret_cast<const float2 *>(stage);
+        // the frame sits `off` bytes into the buffer; pairs that straddle their natural alignment are read
+        // as two scalars (off is group-uniform, so no divergence)
+        const uint32_t off = (uint32_t)(frame_addr(frame) & 15u);
+        if (p.in_i16) {
+          const short *src = reinterpret_cast<const short *>(stage + off);
 #pragma unroll
-        for (int s = 0; s < E; s++) x[s] = src[j + s * T];
+          for (int s = 0; s < E; s++) x[s] = make_float2((float)src[2 * (j + s * T)], (float)src[2 * (j + s * T) + 1]);
+        } else {
+          const float *src = reinterpret_cast<const float *>(stage + off);
+#pragma unroll
+          for (int s = 0; s < E; s++) x[s] = make_float2(src[2 * (j + s * T)], src[2 * (j + s * T) + 1]);
+        }
       }
     }
 
