@@ -301,8 +301,8 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 7: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<7, 8, 16>>(ctx, p, log2n) : launch_small<SmallCfg<7>>(ctx, p);
     case 8: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n) : launch_small<SmallCfg<8>>(ctx, p);
     case 9: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n) : launch_small<SmallCfg<9>>(ctx, p);
-    // 2048..16384 stage frames with bulk copies of the 16-byte aligned superset: any sample alignment
-    case 10: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, 16>>(ctx, p);
+    // 1024..16384 stage frames with bulk copies of the 16-byte aligned superset: any sample alignment
+    case 10: return ctx->use_generic ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, 16>>(ctx, p);
     case 11: return ctx->use_generic ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, 8>>(ctx, p);
     case 12: return ctx->use_generic ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, 4>>(ctx, p);
     case 13: return ctx->use_generic ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);

@@ -16,8 +16,10 @@
 //    one per frame, completion on an mbarrier) issued right after the first barrier of the current
 //    frame.  A register prefetch (ld.global ahead of the statistics) was slower than no prefetch at
 //    all: ptxas shares its six scoreboards between those loads and the LDS/SHFL/ATOMS of the statistics
-//    phase, which then waits for DRAM.  (N = 1024 has no room for the stage: it loads after the stats.)
-//  * two exchange buffers per group, alternated on every exchange: one barrier per exchange; N = 4096
+//    phase, which then waits for DRAM.  Frames that do not start on a 16-byte boundary are copied as
+//    their aligned superset and read at an offset, so any hop / base alignment takes this family.
+//  * two exchange buffers per group, alternated on every exchange: one barrier per exchange (one-warp
+//    groups, N = 1024, reuse a single buffer between __syncwarp()s); N = 4096
 //    pairs the last-pass butterflies j and 256-j in one thread so the real-FFT recombination needs none.
 //  * magnitude = sqrt.approx(|.|^2) * c, where c folds the real-FFT 1/2 and a power-of-two scaling
 //    divisor (divide_by_N always, divide_by_N_sqrt when log2 N is even) into one exact multiply;
@@ -96,16 +98,18 @@ struct V2Cfg {
   // shared memory map (bytes)
   static constexpr size_t OFF_TMSLOT = 0;                                  // TMEM base address (16 B slot)
   static constexpr size_t OFF_GROUPS = 16;
-  static constexpr size_t G_BUF = sizeof(float2) * BUF;                   // x2
+  static constexpr size_t G_BUF = sizeof(float2) * BUF;
+  // two exchange buffers alternated per exchange (one barrier each); one-warp groups (N = 1024) synchronise
+  // with __syncwarp, which is cheap enough to reuse a single buffer and leave room for the staging buffer
+  static constexpr int NBUF = T == 32 ? 1 : 2;
   static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
   static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
   static constexpr size_t G_MISC = sizeof(uint32_t) * 96;
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
-  // N = 2048..8192: the next frame's samples are staged in shared memory by a bulk asynchronous copy
+  // the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
-  static constexpr bool TMA_STAGE = T >= 64;
-  static constexpr size_t G_STAGE = TMA_STAGE ? sizeof(float) * N + 32 : 0;   // samples (+16 B of alignment slack) + mbarrier
-  static constexpr size_t G_BYTES = 2 * G_BUF + G_HIST + G_MISC + G_LIST + G_STAGE;
+  static constexpr size_t G_STAGE = sizeof(float) * N + 32;   // samples (+16 B of alignment slack) + mbarrier
+  static constexpr size_t G_BYTES = NBUF * G_BUF + G_HIST + G_MISC + G_LIST + G_STAGE;
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
 };
 
@@ -180,13 +184,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   const int lane = tid & 31, wig = j >> 5;            // logical warp index inside the group
   unsigned char *gbase = smem + C::OFF_GROUPS + (size_t)g * C::G_BYTES;
   float2 *bufA = reinterpret_cast<float2 *>(gbase);
-  float2 *bufB = reinterpret_cast<float2 *>(gbase + C::G_BUF);
-  uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF);
-  uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST);
-  uint32_t *list = reinterpret_cast<uint32_t *>(gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC);
-  unsigned char *stage = gbase + 2 * C::G_BUF + C::G_HIST + C::G_MISC + C::G_LIST;   // TMA_STAGE only
+  float2 *bufB = reinterpret_cast<float2 *>(gbase + (C::NBUF - 1) * C::G_BUF);   // == bufA when NBUF == 1
+  uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + C::NBUF * C::G_BUF);
+  uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + C::NBUF * C::G_BUF + C::G_HIST);
+  uint32_t *list = reinterpret_cast<uint32_t *>(gbase + C::NBUF * C::G_BUF + C::G_HIST + C::G_MISC);
+  unsigned char *stage = gbase + C::NBUF * C::G_BUF + C::G_HIST + C::G_MISC + C::G_LIST;
   uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + sizeof(float) * N + 16);
-  constexpr bool TMA = C::TMA_STAGE;
   uint32_t phase = 0;              // parity of the mbarrier phase the next wait completes
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
   constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
@@ -256,9 +259,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   auto win1 = [&](int n) -> float { return has_win ? __ldg(p.window + n) : 1.0f; };
   for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
   if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
-  if constexpr (TMA) {
-    if (j == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
-  }
+  if (j == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
   __syncthreads();
   tmem_fence_after_sync();
 
@@ -297,8 +298,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       bulk_copy_g2s(stage, reinterpret_cast<const void *>(a0), bytes, mbar);
     }
   };
-  if constexpr (TMA) { if (j == 0) stage_frame(frame); }
-  else load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j);   // N = 1024: pair-aligned (the host checks)
+  if (j == 0) stage_frame(frame);
   float2 *wbuf = bufA, *obuf = bufB;  // exchange buffers: wbuf is written next
 
   // thread 0: write the record fields of the previous frame (everything except a median written
@@ -327,7 +327,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll 1
   for (;;) {
     const bool more = frame + fstep < p.n_frames;   // group-uniform
-    if constexpr (TMA) {
+    {
       mbar_wait(mbar, phase);
       phase ^= 1u;
       if (al16) {
@@ -378,14 +378,14 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
     group_sync<T>(g);
     // every thread of the group has consumed the staged samples and finished the previous frame
-    if constexpr (TMA) { if (j == 0 && more) stage_frame(frame + fstep); }
+    if (j == 0 && more) stage_frame(frame + fstep);
     if (want_stats && rec_thread) flush_record();
     {
       const float2 *r = wbuf + (j + (j >> 4));
 #pragma unroll
       for (int s = 0; s < 16; s++) x[s] = r[s * PADT];
     }
-    { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+    { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
 
     // ---- pass 2: radix 16, NS = 16 ---------------------------------------------------------------
     {
@@ -408,7 +408,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       // ---- pass 3 (last): two radix-8 butterflies, jbA = j -> x[0..7], jbB -> x[8..15] ------------
 #pragma unroll
       for (int k = 0; k < 8; k++) { x[k] = wbuf[j + 256 * k]; x[8 + k] = wbuf[jbB + 256 * k]; }
-      { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+      { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
       {
         float2 va[8], vb[8];
         va[0] = x[0]; vb[0] = x[8];
@@ -457,7 +457,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
         for (int s = 0; s < 16; s++) x[s] = r[s * T];
       }
-      { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+      { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
 
       if constexpr (C::FOUR) {
         // ---- pass 3: radix 16, NS = 256 (one butterfly per thread) ---------------------------------
@@ -479,7 +479,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
           for (int s = 0; s < 16; s++) x[s] = r[s * T];
         }
-        { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+        { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
         // ---- pass 4 (last): radix R4, NS = 4096; twiddles w_M^(k p) from global memory ---------------
 #pragma unroll
         for (int b = 0; b < C::NB4; b++) {
@@ -549,7 +549,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
         }
       }
-      { float2 *t = wbuf; wbuf = obuf; obuf = t; }
+      { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
     }
     // bin index of val[i]
     auto binof = [&](int i) -> uint32_t {
@@ -1067,9 +1067,6 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
 
 #undef SA_VALID
-    // N = 1024 (no staging buffer, 16 one-warp groups per CTA) loads the next frame after the statistics:
-    // issued before them, the loads share a register scoreboard with that phase and stall it (measured)
-    if constexpr (!TMA) { if (more) load_frame_pairs<E, T>(x, p, frame * p.frame_stride, j); }
     if (!more) break;
   }
   if (want_stats) {
