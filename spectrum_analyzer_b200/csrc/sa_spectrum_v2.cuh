@@ -33,10 +33,10 @@
 //  * NaN/Inf validation (src/lib.rs:168-173) costs nothing on clean frames: any non-finite input
 //    makes every output bin non-finite, so the maximum flags it and only then the group re-reads
 //    its samples to classify NaN vs Inf vs overflow.
-//  * median (src/spectrum.rs:515-524): exact selection.  The keys are histogrammed (256 buckets +
+//  * median (src/spectrum.rs:515-524): exact selection.  The keys are histogrammed (64 buckets +
 //    below/above, unconditional shared-memory atomics) against a window guessed from the previous
 //    frame's median, fused with the min/max/sum pass; after the one statistics barrier every warp
-//    scans the histogram (two levels, 16-byte loads), the (typically < 10) keys of the selected bucket
+//    scans the histogram (two buckets per lane, one warp scan), the (typically < 10) keys of the selected bucket
 //    are appended to a list, and the warp whose thread completes the list ranks it -- nobody waits.
 //    The ranks are verified against the counts; a missed window, an even count, a crowded bucket or a
 //    non-finite frame take the barrier-synchronised exact loop (full-range histogram, narrowing passes).
@@ -76,7 +76,12 @@ struct V2Cfg {
   static constexpr int R4 = FOUR ? M / 4096 : 2;     // radix of the fourth (last) pass when FOUR
   static constexpr int NB4 = 16 / R4;
   static constexpr int BUF = M + M / 16;             // padded float2 elements of one exchange buffer
-  static constexpr int HBITS = 8, NBUCKET = 1 << HBITS;   // median histogram: 256 buckets per pass
+  // median histogram: 64 buckets per pass (measured with the warp-cooperative ranking: 32 buckets 1.49e8,
+  // 64: 1.57e8, 128: 1.56e8, 256: 1.53e8 spectra/s at cfg2; -DSA_HBITS=n rebuilds with another count)
+#ifndef SA_HBITS
+#define SA_HBITS 6
+#endif
+  static constexpr int HBITS = SA_HBITS, NBUCKET = 1 << HBITS;
   static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
   // the per-thread constants (window multipliers, pass twiddles, recombination
   // twiddles: 112 words per thread) in tensor memory, read with tcgen05.ld (sa_tmem.cuh): column
@@ -750,11 +755,43 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         if (gw == 0u && want_median) gw = GW_INIT;
       } else if (use_win && (count & 1u) && !nonfinite) {
         // ---- fast path: no further group barrier -------------------------------------------------
-        // every warp scans the 256 buckets redundantly (8 per lane) and finds the bucket of the middle
-        // rank; the histogram of the previous frame is cleared on the side
-        // two levels: 32 runs of 8 buckets (one per lane, two 16-byte loads), then the 8 buckets of the run
-        // that holds the rank
-        static_assert(HBPL == 8, "two-level scan assumes 8 buckets per lane");
+        // every warp scans the buckets redundantly and finds the bucket of the middle rank; the histogram
+        // of the previous frame is cleared on the side
+        static_assert(HBPL == 8 || HBPL == 4 || HBPL == 2 || HBPL == 1, "scan written for 1, 2, 4 or 8 buckets per lane");
+        uint32_t ba, cnt_a, below_a, om;
+        if constexpr (HBPL <= 4) {
+          // one level: HBPL buckets per lane (one vector load), a warp scan of the lane sums, then the
+          // owner lane's buckets are broadcast and searched
+          uint32_t hb[HBPL];
+          if constexpr (HBPL == 4) { const uint4 h = *reinterpret_cast<const uint4 *>(hist + 1 + lane * 4); hb[0] = h.x; hb[1] = h.y; hb[2] = h.z; hb[3] = h.w; }
+          else if constexpr (HBPL == 2) { const uint2 h = *reinterpret_cast<const uint2 *>(hist + 1 + lane * 2); hb[0] = h.x; hb[1] = h.y; }
+          else hb[0] = hist[1 + lane];
+          const uint32_t nbelow = hist[0];
+          for (int i = j; i < C::HSTRIDE; i += T) hist_other[i] = 0;
+          uint32_t local = 0;
+#pragma unroll
+          for (int b = 0; b < HBPL; b++) local += hb[b];
+          uint32_t incl = local;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+          }
+          om = __ballot_sync(0xffffffffu, nbelow + incl > ra);
+          if (ra < nbelow) om = 0u;
+          const int owner = (__ffs(om) - 1) & 31;
+          uint32_t c = nbelow + __shfl_sync(0xffffffffu, incl - local, owner);
+          ba = (uint32_t)(owner * HBPL); cnt_a = 0; below_a = c;
+          bool found = false;
+#pragma unroll
+          for (int b = 0; b < HBPL; b++) {
+            const uint32_t h = __shfl_sync(0xffffffffu, hb[b], owner);
+            const bool here = !found && (c + h > ra);
+            if (here) { ba = (uint32_t)(owner * HBPL + b); cnt_a = h; below_a = c; }
+            found = found || here;
+            c += h;
+          }
+        } else {
         const uint4 h0 = *reinterpret_cast<const uint4 *>(hist + 1 + lane * 8);
         const uint4 h1 = *reinterpret_cast<const uint4 *>(hist + 5 + lane * 8);
         const uint32_t nbelow = hist[0];
@@ -767,7 +804,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           if (lane >= off) incl += o;
         }
         // first run whose inclusive count exceeds the rank (none: the window missed the middle rank)
-        uint32_t om = __ballot_sync(0xffffffffu, nbelow + incl > ra);
+        om = __ballot_sync(0xffffffffu, nbelow + incl > ra);
         if (ra < nbelow) om = 0u;
         const int owner = (__ffs(om) - 1) & 31;
         const uint32_t c0o = nbelow + __shfl_sync(0xffffffffu, incl - local, owner);
@@ -780,9 +817,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         }
         const uint32_t om8 = __ballot_sync(0xffffffffu, c0o + incl8 > ra) & 0xffu;
         const int b8 = (__ffs(om8) - 1) & 7;
-        const uint32_t ba = (uint32_t)(owner * 8 + b8);
-        const uint32_t cnt_a = __shfl_sync(0xffffffffu, h8, b8);
-        const uint32_t below_a = c0o + __shfl_sync(0xffffffffu, incl8 - h8, b8);
+        ba = (uint32_t)(owner * 8 + b8);
+        cnt_a = __shfl_sync(0xffffffffu, h8, b8);
+        below_a = c0o + __shfl_sync(0xffffffffu, incl8 - h8, b8);
+        }
         const uint32_t lo_a = winL + (ba << shw), bw = (1u << shw) - 1u;
         if (om != 0u && cnt_a <= 32u) {
           if (shw == 0) {
