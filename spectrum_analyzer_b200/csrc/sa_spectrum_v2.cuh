@@ -197,7 +197,16 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + sizeof(float) * N + 16);
   uint32_t phase = 0;              // parity of the mbarrier phase the next wait completes
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
-  constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << 17;   // median window half-width (key units)
+#ifndef SA_GW_MIN_LOG2
+#define SA_GW_MIN_LOG2 17
+#endif
+#ifndef SA_GW_SHRINK
+#define SA_GW_SHRINK 6
+#endif
+#ifndef SA_GW_GROW
+#define SA_GW_GROW 2
+#endif
+  constexpr uint32_t GW_INIT = 1u << 20, GW_MIN = 1u << SA_GW_MIN_LOG2;   // median window half-width (key units)
   uint32_t gw = 0u;                // 0: no guess yet (first frame of the group)
   int par = 0;                     // which of the two histograms this frame uses
   // record fields written one barrier later (after every thread finished the frame) by the first lane
@@ -635,7 +644,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       par ^= 1;
       const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;   // middle ranks (0-based)
       // Median window guess: keys within gw of the previous frame's median.  The fused pass below
-      // histograms all keys against that window (below / 256 buckets / above); the selection stays
+      // histograms all keys against that window (below / NBUCKET buckets / above); the selection stays
       // exact because the ranks are verified against the counts, with the full-range pass as fallback.
       const bool use_win = want_median && gw != 0u;
       const uint32_t gk = use_win ? misc[MI_GUESS] : 0u;
@@ -904,7 +913,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
             if (rec_thread) pend_med = false;
           }
           if (rec_thread) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; }
-          gw = max(gw - (gw >> 6), GW_MIN);
+          gw = max(gw - (gw >> SA_GW_SHRINK), GW_MIN);
         } else {
           // the guessed window missed the middle rank, or its bucket is crowded: exact loop below
           group_sync<T>(g);                                   // every warp has finished scanning
@@ -1058,7 +1067,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         }
         // adapt the window for the next frame (all values here are group-uniform)
         if (gw == 0u) gw = GW_INIT;
-        else if (win_failed) gw = (gw < (1u << 28)) ? gw << 2 : gw;
+        else if (win_failed) gw = (gw < (1u << 28)) ? gw << SA_GW_GROW : gw;
         if (!synced) group_sync<T>(g);
         if (j == 0) {
           // a group barrier has passed since the arg-bin / flag atomics: write the record now
