@@ -215,7 +215,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   bool pend = false, pend_med = false;
   u64 pend_cur = 0;
   uint32_t pend_kmn = 0, pend_kmx = 0, pend_medkey = 0;
-  float pend_sum = 0.f;
+  float pend_avg = 0.f;   // the division happens in the statistics phase, off the exchange critical path
 
   // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
@@ -327,7 +327,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       r0.w = mm ? misc[MI_ARGMAX] : 0u;
       uint32_t *rec = reinterpret_cast<uint32_t *>(&p.stats[pend_cur]);
       *reinterpret_cast<uint4 *>(rec) = r0;
-      rec[4] = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(pend_sum, (float)count)) : 0u;
+      rec[4] = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(pend_avg) : 0u;
       if (pend_med) rec[5] = want_median ? __float_as_uint(v2_unkey<MODE>(pend_medkey)) : 0u;
       const uint32_t fl = misc[MI_FLAGS];
       const uint32_t st = (fl & 1u) ? SA_ERR_NAN_VALUES : (fl & 2u) ? SA_ERR_INFINITY_VALUES
@@ -754,7 +754,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       if (!want_median || (all_equal && !nonfinite)) {
         // nothing to select: thread 0 writes the whole record one barrier later
         if (rec_thread) {
-          pend = true; pend_med = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; pend_medkey = kmn;
+          pend = true; pend_med = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_avg = __fdiv_rn(sum, (float)count); pend_medkey = kmn;
           if (want_median) misc[MI_GUESS] = kmn;
         }
         if (use_win) {   // the fused pass dirtied this histogram: every warp clears a quarter, used again in 2 frames
@@ -912,7 +912,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
             }
             if (rec_thread) pend_med = false;
           }
-          if (rec_thread) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_sum = sum; }
+          if (rec_thread) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_avg = __fdiv_rn(sum, (float)count); }
           gw = max(gw - (gw >> SA_GW_SHRINK), GW_MIN);
         } else {
           // the guessed window missed the middle rank, or its bucket is crowded: exact loop below
