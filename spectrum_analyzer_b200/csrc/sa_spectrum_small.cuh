@@ -198,14 +198,6 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
     for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
     vmid = scale1(vmid);
 
-    if (cur_active) {
-      float *dst = p.out_vals + cur * p.out_stride - lo;
-#pragma unroll
-      for (int i = 0; i < E; i++)
-        if (SA_VALID(i)) dst[binof(i)] = val[i];
-      if (valid_mid) dst[M / 2] = vmid;
-    }
-
     // ---- statistics --------------------------------------------------------------------------------------
     if (want_stats) {
       const uint32_t ra = (count & 1u) ? count / 2 : count / 2 - 1, rb = count / 2;
@@ -440,6 +432,14 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
       }
       if (j == 0) { misc[SM_ARGMIN] = 0xffffffffu; misc[SM_ARGMAX] = 0u; misc[SM_FLAGS] = 0u; }
       __syncwarp();
+    }
+    // stores after the statistics (whose shuffle / shared-memory chains would queue behind them, cf. sa_spectrum_v2.cuh)
+    if (cur_active) {
+      float *dst = p.out_vals + cur * p.out_stride - lo;
+#pragma unroll
+      for (int i = 0; i < E; i++)
+        if (SA_VALID(i)) dst[binof(i)] = val[i];
+      if (valid_mid) dst[M / 2] = vmid;
     }
 #undef SA_VALID
     if (!more) break;
