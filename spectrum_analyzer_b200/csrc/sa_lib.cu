@@ -246,6 +246,10 @@ int launch_small_inst(sa_ctx *ctx, const V2Params &P) {
     int per_sm = 0;
     SA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::NT, C::SMEM_TOTAL));
     if (per_sm < 1) { g_last_error = "small kernel does not fit on an SM"; return SA_ERR_CUDA; }
+    // The occupancy calculator answers 1 for kernels that allocate tensor memory; two CTAs of 256 threads
+    // (<= 128 registers by __launch_bounds__, 48 KB of shared memory, 128 of 512 TMEM columns each) do fit.
+    // The grid is persistent (frames strided by gridDim), so a CTA that had to wait would still be correct.
+    per_sm = std::max(per_sm, 2);
     plan.max_blocks = per_sm * ctx->num_sms;
     plan.ready = true;
   }

@@ -26,10 +26,12 @@ struct SmallCfg {
   static constexpr int HS = NB + 8;                     // [below | NB buckets | above | pad]
   static constexpr int NTW2 = (R2 - 1) * 16, NTWR = M / 2;
   static_assert(T >= 2 && T <= 16, "small family covers N = 64..512");
-  static constexpr size_t OFF_WIN = 0;
-  static constexpr size_t OFF_TW2 = OFF_WIN + sizeof(float) * N;
-  static constexpr size_t OFF_TWR = OFF_TW2 + sizeof(float2) * NTW2;
-  static constexpr size_t OFF_WARPS = (OFF_TWR + sizeof(float2) * NTWR + 15) & ~size_t(15);
+  // per-thread constants (window multipliers of the 32 samples a lane owns, last-pass twiddles, recombination
+  // twiddles) live in tensor memory, as in the tuned family (sa_tmem.cuh): columns [0,32) window |
+  // [32,62) pass-2 twiddles, entry b*(R2-1) + k-1 | [64,80) recombination.  They depend on lane % T only.
+  static constexpr int TM_COLS = 128, TM_WIN = 0, TM_TW2 = 32, TM_TWR = 64;
+  static constexpr size_t OFF_TMSLOT = 0;
+  static constexpr size_t OFF_WARPS = 16;
   static constexpr size_t W_BUF = sizeof(float2) * FBUF * FPW;
   static constexpr size_t W_HIST = sizeof(uint32_t) * HS * FPW;
   static constexpr size_t W_MISC = sizeof(uint32_t) * 16 * FPW;
@@ -41,15 +43,10 @@ struct SmallCfg {
 enum { SM_ARGMIN = 0, SM_ARGMAX = 1, SM_LCOUNT = 2, SM_FLAGS = 3, SM_RESA = 4, SM_RESB = 5 };
 
 template <class C, int MODE, bool FULL>
-__global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params P) {
+__device__ __forceinline__ void spectrum_body_small(const V2Params &P, unsigned char *smem, const uint32_t tm_base) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, FPW = C::FPW, R2 = C::R2, NB2 = C::NB2;
   constexpr bool ODD = FULL;                         // FrequencyLimit::All keeps N/2+1 bins: one middle rank
   constexpr uint32_t LIST_MAX = (2 * T > 8) ? 2 * T : 8;   // larger buckets are narrowed by another pass
-  extern __shared__ __align__(16) unsigned char smem[];
-  float *s_win = reinterpret_cast<float *>(smem + C::OFF_WIN);
-  float2 *s_tw2 = reinterpret_cast<float2 *>(smem + C::OFF_TW2);
-  float2 *s_twr = reinterpret_cast<float2 *>(smem + C::OFF_TWR);
-
   const SpectrumParams &p = P.b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane / T, j = lane - fl * T;                       // frame slot in the warp, lane in the group
@@ -61,12 +58,44 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
   uint32_t *list = reinterpret_cast<uint32_t *>(wbase + C::W_BUF + C::W_HIST + C::W_MISC) + fl * 32;
 
   const bool has_win = p.window != nullptr;
-  for (int i = tid; i < N; i += C::NT) s_win[i] = has_win ? __ldg(p.window + i) : 1.0f;
-  for (int i = tid; i < C::NTW2; i += C::NT) s_tw2[i] = __ldg(P.tw2 + i);
-  for (int i = tid; i < C::NTWR; i += C::NT) s_twr[i] = __ldg(P.twr + i);
+  const uint32_t ta = tmem_addr(tm_base, warp, 0);   // this thread's table row (lane quadrant warp % 4)
+  if (tid < 128) {   // warps 0..3 fill the four lane quadrants; every warp of the CTA reads the same columns
+    float v[16];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const float2 w = has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + j + (8 * h + s) * T) : make_float2(1.f, 1.f);
+        v[2 * s] = w.x; v[2 * s + 1] = w.y;
+      }
+      tmem_st16(ta + C::TM_WIN + 16 * h, v);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const int e = 8 * h + s;
+        float2 w = make_float2(0.f, 0.f);
+        if (e < NB2 * (R2 - 1)) {
+          const int b = e / (R2 - 1), k = e % (R2 - 1) + 1;
+          w = __ldg(P.tw2 + (k - 1) * 16 + j + b * T);
+        }
+        v[2 * s] = w.x; v[2 * s + 1] = w.y;
+      }
+      tmem_st16(ta + C::TM_TW2 + 16 * h, v);
+    }
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const float2 w = __ldg(P.twr + j + s * T);
+      v[2 * s] = w.x; v[2 * s + 1] = w.y;
+    }
+    tmem_st16(ta + C::TM_TWR, v);
+  }
+  tmem_fence_before_sync();
   for (int i = j; i < C::HS; i += T) hist[i] = 0;
   if (j == 0) { misc[SM_ARGMIN] = 0xffffffffu; misc[SM_ARGMAX] = 0u; misc[SM_LCOUNT] = 0u; misc[SM_FLAGS] = 0u; }
   __syncthreads();
+  tmem_fence_after_sync();
 
   const uint32_t lo = p.bin_lo, hi = p.bin_hi;
   const uint32_t count = hi - lo + 1;
@@ -92,11 +121,14 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
 #pragma unroll 1
   for (;;) {
     // ---- window (src/windows.rs), exact f32 multiply ---------------------------------------------
+    {
+      float w[32];
+      tmem_ld32(ta + C::TM_WIN, w);
 #pragma unroll
-    for (int s = 0; s < E; s++) {
-      const float2 w = *reinterpret_cast<const float2 *>(s_win + 2 * (j + s * T));
-      x[s].x = __fmul_rn(w.x, x[s].x);
-      x[s].y = __fmul_rn(w.y, x[s].y);
+      for (int s = 0; s < E; s++) {
+        x[s].x = __fmul_rn(w[2 * s], x[s].x);
+        x[s].y = __fmul_rn(w[2 * s + 1], x[s].y);
+      }
     }
     // ---- pass 1: radix 16 ---------------------------------------------------------------------------
     dft16(x);
@@ -113,14 +145,18 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
     }
     __syncwarp();
     // ---- pass 2 (last): radix T, NS = 16; x[s] = Z[j + s*T] afterwards ------------------------------
+    float t2[32];
+    tmem_ld32(ta + C::TM_TW2, t2);   // w_M^(k (j + b T)), entry b*(R2-1) + k-1
 #pragma unroll
     for (int b = 0; b < NB2; b++) {
       float2 v[R2];
 #pragma unroll
       for (int k = 0; k < R2; k++) v[k] = x[b + k * NB2];
-      const int jb = j + b * T;  // < 16
 #pragma unroll
-      for (int k = 1; k < R2; k++) v[k] = cmul(v[k], s_tw2[(k - 1) * 16 + jb]);
+      for (int k = 1; k < R2; k++) {
+        const int e = b * (R2 - 1) + k - 1;
+        v[k] = cmul(v[k], make_float2(t2[2 * e], t2[2 * e + 1]));
+      }
       dft<R2>(v);
 #pragma unroll
       for (int k = 0; k < R2; k++) x[b + k * NB2] = v[k];
@@ -130,6 +166,8 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
     float vmid = 0.f;
     {
       const int pl = (T - j) & (T - 1);
+      float tr[16];
+      tmem_ld16(ta + C::TM_TWR, tr);   // W_N^(j + s T)
 #pragma unroll
       for (int s = 0; s < E / 2; s++) {
         float2 bq;
@@ -137,7 +175,7 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
         bq.y = __shfl_sync(0xffffffffu, x[15 - s].y, pl, T);
         if (j == 0 && s > 0) bq = x[16 - s];   // lane 0 pairs k = s*T with (16-s)*T, its own slot
         const float2 a = x[s];
-        const float2 w = s_twr[j + s * T];
+        const float2 w = make_float2(tr[2 * s], tr[2 * s + 1]);
         const float2 cb = make_float2(bq.x, -bq.y);
         const float2 pp = add2(a, cb), qq = sub2(a, cb);
         const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
@@ -247,7 +285,7 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
         if (nonfinite) {
           uint32_t f = 4u;
           for (int n = j; n < N; n += T) {
-            const float v = __fmul_rn(s_win[n], load_sample(p, cur * p.frame_stride + n));
+            const float v = __fmul_rn(has_win ? __ldg(p.window + n) : 1.0f, load_sample(p, cur * p.frame_stride + n));
             if (v != v) f |= 1u;
             if (fabsf(v) == INFINITY) f |= 2u;
           }
@@ -444,6 +482,21 @@ __global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params
 #undef SA_VALID
     if (!more) break;
   }
+}
+
+template <class C, int MODE, bool FULL>
+__global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t *slot = reinterpret_cast<uint32_t *>(smem + C::OFF_TMSLOT);
+  if (threadIdx.x < 32) tmem_alloc<C::TM_COLS>(slot);
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  const uint32_t tm_base = *slot;
+  spectrum_body_small<C, MODE, FULL>(P, smem, tm_base);
+  tmem_fence_before_sync();
+  __syncthreads();   // warps finish at different times: release the allocation when all are done
+  if (threadIdx.x < 32) tmem_dealloc<C::TM_COLS>(tm_base);
 }
 
 }  // namespace sa
