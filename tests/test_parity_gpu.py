@@ -340,3 +340,22 @@ def test_frame_counts_around_grid_boundaries(gpu_ctx, n, counts):
     assert code == 0 and np.all(ostatus == 0)
     gv = ref.vals.cpu().numpy()[total - 4:, : ref.n_bins]
     assert np.all(np.abs(gv - ov) <= MAG_RTOL * ov.max(axis=1, keepdims=True))
+
+
+@pytest.mark.parametrize("n", [256, 1024, 2048, 4096, 8192, 16384])
+def test_repeat_launch_is_bit_identical(gpu_ctx, n):
+    """Two launches on the same input give the same bits -- values and the whole 32-byte records.  (The kernels
+    use shared-memory atomics, 'first warp to finish' protocols and asynchronous copies; any race in them would
+    show up here as a difference between runs.)"""
+    import torch
+    m = sa()
+    frames = (1 << 22) // n + 13
+    x = torch.from_numpy(noise(frames, n, seed=n + 1)).cuda()
+    kw = dict(window=O.WINDOW_HANN, n=n, frame_stride=n, n_frames=frames, stats=7)
+    runs = []
+    for _ in range(3):
+        r = m.samples_fft_to_spectrum_batched(x, 44100, m.FrequencyLimit.All, m.scaling.scale_20_times_log10, **kw)
+        torch.cuda.synchronize()
+        runs.append((r.vals.view(torch.int32).clone(), r.stats.clone()))
+    for v, s in runs[1:]:
+        assert torch.equal(v, runs[0][0]) and torch.equal(s, runs[0][1])
