@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <string>
 #include <utility>
@@ -73,6 +74,9 @@ struct sa_ctx {
   size_t slot_in_bytes = 0, slot_out_bytes = 0, slot_stats_bytes = 0;
   cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
   bool pipeline_ready = false;
+  // single-frame call (sa_spectrum_single): one pinned host block and one device block, reused
+  unsigned char *single_pin = nullptr, *single_dev = nullptr;
+  size_t single_bytes = 0;
 };
 
 namespace {
@@ -490,6 +494,8 @@ int sa_ctx_destroy(sa_ctx *ctx) {
     if (ctx->pipeline_ready) { cudaEventDestroy(ctx->ev_h2d[s]); cudaEventDestroy(ctx->ev_comp[s]); cudaEventDestroy(ctx->ev_d2h[s]); }
   }
   if (ctx->pipeline_ready) { cudaStreamDestroy(ctx->h2d); cudaStreamDestroy(ctx->d2h); }
+  if (ctx->single_pin) cudaFreeHost(ctx->single_pin);
+  if (ctx->single_dev) cudaFree(ctx->single_dev);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SA_OK;
@@ -668,12 +674,17 @@ int sa_spectrum_single(sa_ctx *ctx, const float *h_samples, uint64_t n_samples, 
   if (n_samples < 2) return SA_ERR_TOO_FEW_SAMPLES;
   if (!h_samples) return SA_ERR_INVALID_ARGUMENT;
   {
+    // the multiplier only matters where a sample is infinite (w == 0 turns Inf into NaN): the window's cosf is
+    // not evaluated for the finite samples of an ordinary call
     bool any_nan = false, any_inf = false;
     for (uint64_t i = 0; i < n_samples; i++) {
-      float v = h_samples[i];
-      if (window_kind != SA_WINDOW_NONE) v = sa_host::window_multiplier(window_kind, (uint32_t)i, (uint32_t)n_samples) * v;
-      any_nan |= std::isnan(v);
-      any_inf |= std::isinf(v);
+      const float v = h_samples[i];
+      if (std::fabs(v) <= std::numeric_limits<float>::max()) continue;   // finite
+      if (std::isnan(v)) { any_nan = true; continue; }
+      const float w = window_kind == SA_WINDOW_NONE ? 1.0f : sa_host::window_multiplier(window_kind, (uint32_t)i, (uint32_t)n_samples);
+      const float wv = w * v;
+      any_nan |= std::isnan(wv);
+      any_inf |= std::isinf(wv);
     }
     if (any_nan) return SA_ERR_NAN_VALUES;
     if (any_inf) return SA_ERR_INFINITY_VALUES;
@@ -682,13 +693,37 @@ int sa_spectrum_single(sa_ctx *ctx, const float *h_samples, uint64_t n_samples, 
   const int e = validate_call(n_samples, sampling_rate, limit_kind, limit_lo, limit_hi, window_kind, scaling_kind, &lo, &nb);
   if (e != SA_OK) return e;
   if (!h_vals) return SA_ERR_INVALID_ARGUMENT;
-  sa_frame_stats st;
-  std::memset(&st, 0, sizeof st);
   const uint32_t n = (uint32_t)n_samples;
-  const int r = sa_spectrum_batched_host(ctx, h_samples, 1, n, n, sampling_rate, limit_kind, limit_lo, limit_hi,
-                                         window_kind, scaling_kind, SA_STATS_ALL, h_vals, nb, &st, nullptr, nullptr);
-  if (r != SA_OK) return r;
+  // latency path: samples -> pinned block -> device, one launch, [values | record] back in one copy
+  SA_CUDA(cudaSetDevice(ctx->device));
+  const size_t in_bytes = ((size_t)n * sizeof(float) + 255) & ~(size_t)255;
+  const size_t val_bytes = ((size_t)nb * sizeof(float) + 31) & ~(size_t)31;
+  const size_t total = in_bytes + val_bytes + sizeof(sa_frame_stats);
+  if (ctx->single_bytes < total) {
+    if (ctx->single_pin) SA_CUDA(cudaFreeHost(ctx->single_pin));
+    if (ctx->single_dev) SA_CUDA(cudaFree(ctx->single_dev));
+    ctx->single_pin = ctx->single_dev = nullptr;
+    ctx->single_bytes = 0;
+    SA_CUDA(cudaMallocHost(&ctx->single_pin, total));
+    SA_CUDA(cudaMalloc(&ctx->single_dev, total));
+    ctx->single_bytes = total;
+  }
+  std::memcpy(ctx->single_pin, h_samples, (size_t)n * sizeof(float));
+  SA_CUDA(cudaMemcpyAsync(ctx->single_dev, ctx->single_pin, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  float *d_vals = reinterpret_cast<float *>(ctx->single_dev + in_bytes);
+  sa_frame_stats *d_st = reinterpret_cast<sa_frame_stats *>(ctx->single_dev + in_bytes + val_bytes);
+  SpectrumParams p;
+  int pe = fill_params(ctx, p, ctx->single_dev, 0, 1, n, n, window_kind, scaling_kind, SA_STATS_ALL, d_vals, nb, d_st, lo, nb);
+  if (pe != SA_OK) return pe;
+  pe = launch_spectrum(ctx, p, log2_exact(n));
+  if (pe != SA_OK) return pe;
+  SA_CUDA(cudaMemcpyAsync(ctx->single_pin + in_bytes, ctx->single_dev + in_bytes, val_bytes + sizeof(sa_frame_stats),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  SA_CUDA(cudaStreamSynchronize(ctx->stream));
+  sa_frame_stats st;
+  std::memcpy(&st, ctx->single_pin + in_bytes + val_bytes, sizeof st);
   if (st.status != SA_OK) return (int)st.status;
+  std::memcpy(h_vals, ctx->single_pin + in_bytes, (size_t)nb * sizeof(float));
   if (h_freqs) sa_bin_frequencies(n, sampling_rate, lo, nb, h_freqs);
   if (n_bins) *n_bins = nb;
   if (h_stats) *h_stats = st;
