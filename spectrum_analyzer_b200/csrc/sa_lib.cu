@@ -595,7 +595,8 @@ static int spectrum_batched_host_impl(sa_ctx *ctx, const void *h_samples_v, int 
   SA_CUDA(cudaSetDevice(ctx->device));
 
   // chunking: ~64 MiB of unique input per chunk
-  const uint64_t target = 64ull << 20;
+  // input bytes per pipeline chunk (SA_PIPE_CHUNK_MB overrides for tuning)
+  static const uint64_t target = [] { const char *e = getenv("SA_PIPE_CHUNK_MB"); return (uint64_t)(e ? std::max(1, atoi(e)) : 64) << 20; }();
   uint64_t chunk = std::max<uint64_t>(1, target / (frame_stride * esz));
   chunk = std::min(chunk, n_frames);
   const size_t in_bytes = ((chunk - 1) * frame_stride + n) * esz;
