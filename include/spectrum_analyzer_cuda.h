@@ -151,6 +151,10 @@ int sa_bin_frequencies(uint32_t n, uint32_t sampling_rate, uint32_t bin_lo, uint
  *               then per-frame validation results are not reported)
  * Host outputs: *bin_lo, *n_bins (may be NULL).
  * n must be a power of two in [2, 32768]; out_stride >= n_bins.
+ * Alignment: none beyond the element type's.  Frames of n >= 1024 samples are staged by bulk
+ * copies of their 16-byte aligned superset, which may read up to 15 bytes before the first and
+ * after the last sample of the batch (inside the allocation granule of any CUDA allocation, never
+ * written, never used); 16-byte aligned frames (base pointer and hop) take the fastest path.
  */
 int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, uint32_t n,
                         uint64_t frame_stride, uint32_t sampling_rate, int limit_kind,
