@@ -309,20 +309,15 @@ class FrequencySpectrum:
 
     # -- FrequencySpectrum::apply_scaling_fn (src/spectrum.rs:128-168), on the device --
     def apply_scaling_fn(self, scaling_fn) -> None:
-        import torch
         kinds = scaling_fn.kinds if isinstance(scaling_fn, _ScalingChain) else (_scaling_kind(scaling_fn),)
         ctx = self._ctx or default_context()
-        dev = torch.device("cuda", ctx.device)
-        vals = torch.from_numpy(self._vals.copy()).to(dev)
-        st = torch.from_numpy(np.frombuffer(np.asarray(self._stats).tobytes(), np.uint8).copy()).to(dev)
-        torch.cuda.synchronize(dev)
+        vals = np.ascontiguousarray(self._vals, dtype=np.float32).copy()
+        st = np.array([self._stats], dtype=A.FRAME_STATS_DTYPE)
         karr = (C.c_int * max(len(kinds), 1))(*kinds)
-        _check(A.load().sa_apply_scaling_chain_batched(ctx._h, vals.data_ptr(), 1, vals.numel(), vals.numel(),
-                                                       self._bin_lo, self._n, karr, len(kinds), A.STATS_ALL,
-                                                       st.data_ptr()))
-        ctx.sync()
-        self._vals = vals.cpu().numpy()
-        self._stats = np.frombuffer(st.cpu().numpy().tobytes(), A.FRAME_STATS_DTYPE)[0]
+        _check(A.load().sa_apply_scaling_chain_host(ctx._h, vals.ctypes.data, 1, vals.size, vals.size, self._bin_lo,
+                                                    self._n, karr, len(kinds), A.STATS_ALL, st.ctypes.data))
+        self._vals = vals
+        self._stats = st[0]
 
 
 # ---------------------------------------------------------------------------------------------
