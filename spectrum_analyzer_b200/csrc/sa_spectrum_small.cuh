@@ -232,9 +232,18 @@ __device__ __forceinline__ void spectrum_body_small(const V2Params &P, unsigned 
       else if constexpr (MODE == SCALE_ZERO_ONE) return umax != 0.0f ? __fdiv_rn(v, umax) : 0.0f;
       else return (v == 0.0f) ? 0.0f : __fmul_rn(20.0f, log10f_musl(v));
     };
+    // zero-to-one: one reciprocal per frame + exact FMA correction instead of 17 IEEE divisions (sa_spectrum_v2.cuh);
+    // lanes of different frames may take different branches, each branch is the same exact function
+    if (MODE == SCALE_ZERO_ONE && frame_max_is_fast_divisor(umax)) {
+      const float rmax = __frcp_rn(umax);
 #pragma unroll
-    for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
-    vmid = scale1(vmid);
+      for (int i = 0; i < E; i++) val[i] = div_by_frame_max(val[i], umax, rmax);
+      vmid = div_by_frame_max(vmid, umax, rmax);
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
+      vmid = scale1(vmid);
+    }
 
     // ---- statistics --------------------------------------------------------------------------------------
     if (want_stats) {
