@@ -19,8 +19,8 @@
 //    phase, which then waits for DRAM.  Frames that do not start on a 16-byte boundary are copied as
 //    their aligned superset and read at an offset, so any hop / base alignment takes this family.
 //  * two exchange buffers per group, alternated on every exchange: one barrier per exchange (one-warp
-//    groups, N = 1024, reuse a single buffer between __syncwarp()s); N = 4096
-//    pairs the last-pass butterflies j and 256-j in one thread so the real-FFT recombination needs none.
+//    groups, N = 1024, reuse a single buffer between __syncwarp()s); every size but N = 8192 pairs
+//    mirrored last-pass butterflies in one thread so the real-FFT recombination needs no exchange.
 //  * magnitude = sqrt.approx(|.|^2) * c, where c folds the real-FFT 1/2 and a power-of-two scaling
 //    divisor (divide_by_N always, divide_by_N_sqrt when log2 N is even) into one exact multiply;
 //    other divisors use an exactly-rounded FMA division.
@@ -96,7 +96,7 @@ struct V2Cfg {
   static constexpr int TM_JSETS = T > 128 ? T / 128 : 1;      // column sets needed to cover j >= 128
   static constexpr int TM_SETS = TM_JSETS * NROT, TM_SET_COLS = 128, TM_COLS = TM_SETS * TM_SET_COLS;
   static_assert(TM_COLS <= 512 && G_ / GPQ >= NROT, "TMEM table layout");
-  static constexpr int TM_WIN = 0, TM_TW2 = 32, TM_TW3 = 64, TM_TWR = 96;
+  static constexpr int TM_WIN = 0, TM_TW2 = 32, TM_TW3 = 64, TM_TWR = 96, TM_TW4 = 112;   // TM_TW4: N = 16384 only
   static constexpr int NTW2 = 15 * 16, NTW3 = (R3 - 1) * 256, NTWR = M / 2, NTW4 = FOUR ? (R4 - 1) * 4096 : 0;
   static_assert(T % 32 == 0 && T >= 32 && T <= 512, "v2 covers N = 1024..16384");
   static_assert(NT <= 1024 && (T == 32 || G_ <= 15), "named barriers 1..15");
@@ -196,6 +196,13 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // outputs are exactly each other's mirror bins Z[k] <-> Z[M-k]: the real-FFT recombination then
   // needs no exchange and no barrier.
   constexpr bool MIRROR = (NB3 == 2);
+  // The same idea for the other sizes whose last pass runs >= 2 butterflies per thread (N = 1024, 2048 and the
+  // radix-2 fourth pass of N = 16384): with S = (butterflies of the last pass) = LNB*T, thread j owns the LNB/2
+  // butterflies A_i = j + i*T and their mirrors B_i = S - A_i (thread 0: B_0 = S/2, the self-mirrored one, and
+  // A_0 = 0 pairs with itself), so every pair Z[k], Z[M-k] meets in one thread and the recombination needs no
+  // exchange.  N = 8192 (one radix-16 butterfly per thread) keeps the exchange.
+  constexpr int LR = C::FOUR ? C::R4 : R3, LNB = C::FOUR ? C::NB4 : NB3, LS = LNB * T, LH = LNB / 2;
+  constexpr bool MIRG = !MIRROR && LNB >= 2;
 
   const SpectrumParams &p = P.b;
   const int tid = threadIdx.x;
@@ -236,6 +243,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
   const int jbB = j ? 256 - j : 128;   // MIRROR: second last-pass butterfly of this thread
+  auto bfA = [&](int i) -> int { return j + i * T; };                                         // MIRG
+  auto bfB = [&](int i) -> int { return j ? LS - (j + i * T) : (i ? LS - i * T : LS / 2); };  // MIRG
   const uint32_t ta = tmem_addr(tm_base, tid >> 5, (rot * C::TM_JSETS + (j >> 7)) * C::TM_SET_COLS);   // this thread's table row
   {
     // the first NROT * max(T,128) threads cover every (lane quadrant, column set) once
@@ -268,7 +277,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           float2 w = make_float2(0.f, 0.f);
           if (e < NB3 * (R3 - 1)) {
             const int b = e / (R3 - 1), k = e % (R3 - 1) + 1;
-            const int jb = MIRROR ? (b ? jbB : j) : C::FOUR ? (j & 255) : j + b * T;
+            const int jb = MIRROR ? (b ? jbB : j) : C::FOUR ? (j & 255) : MIRG ? ((b & 1) ? bfB(b >> 1) : bfA(b >> 1)) : j + b * T;
             w = __ldg(P.tw3 + (k - 1) * 256 + jb);
           }
           v[2 * s] = w.x; v[2 * s + 1] = w.y;
@@ -277,11 +286,21 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
 #pragma unroll
       for (int s = 0; s < 8; s++) {   // recombination twiddles W_N^k of the 8 bin pairs this thread owns
-        const int k = MIRROR ? ((s & 1) ? jbB : j) + 256 * (s >> 1) : j + s * T;
+        int k = MIRROR ? ((s & 1) ? jbB : j) + 256 * (s >> 1) : j + s * T;
+        if constexpr (MIRG) { const int i = s / LR, rem = s % LR; k = ((rem & 1) ? bfB(i) : bfA(i)) + (rem >> 1) * LS; }
         const float2 w = __ldg(P.twr + k);
         v[2 * s] = w.x; v[2 * s + 1] = w.y;
       }
       tmem_st16(ta + C::TM_TWR, v);
+      if constexpr (C::FOUR) {   // fourth pass (radix 2): w_M^(jb) for the 8 butterflies in the order A_0, B_0, A_1, ...
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+          const int jb = (s & 1) ? bfB(s >> 1) : bfA(s >> 1);
+          const float2 w = __ldg(P.tw4 + jb);
+          v[2 * s] = w.x; v[2 * s + 1] = w.y;
+        }
+        tmem_st16(ta + C::TM_TW4, v);
+      }
     }
     tmem_fence_before_sync();
   }
@@ -482,7 +501,18 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         }
       }
     } else {
-      {
+      // inputs of the last pass in the order A_0, B_0, A_1, B_1, ...: butterfly b reads positions b + k*LS
+      auto read_mirror_list = [&]() {
+#pragma unroll
+        for (int i = 0; i < LH; i++) {
+          const float2 *ra = wbuf + bfA(i), *rb = wbuf + bfB(i);
+#pragma unroll
+          for (int k = 0; k < LR; k++) { x[(2 * i) * LR + k] = ra[k * LS]; x[(2 * i + 1) * LR + k] = rb[k * LS]; }
+        }
+      };
+      if constexpr (MIRG && !C::FOUR) {
+        read_mirror_list();
+      } else {
         const float2 *r = wbuf + j;
 #pragma unroll
         for (int s = 0; s < 16; s++) x[s] = r[s * T];
@@ -504,82 +534,117 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           for (int k = 0; k < 16; k++) w[256 * k] = x[k];
         }
         group_sync<T>(g);
-        {
-          const float2 *r = wbuf + j;
-#pragma unroll
-          for (int s = 0; s < 16; s++) x[s] = r[s * T];
-        }
+        read_mirror_list();
         { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
-        // ---- pass 4 (last): radix R4, NS = 4096; twiddles w_M^(k p) from global memory ---------------
-#pragma unroll
-        for (int b = 0; b < C::NB4; b++) {
-          float2 v[C::R4];
-#pragma unroll
-          for (int k = 0; k < C::R4; k++) v[k] = x[b + k * C::NB4];
-          const int jb = j + b * T;  // < 4096
-#pragma unroll
-          for (int k = 1; k < C::R4; k++) v[k] = cmul(v[k], __ldg(P.tw4 + (k - 1) * 4096 + jb));
-          dft<C::R4>(v);
-#pragma unroll
-          for (int k = 0; k < C::R4; k++) x[b + k * C::NB4] = v[k];
-        }
-      } else {
-        // ---- pass 3 (last): radix R3, NS = 256; results stay in registers: x[s] = Z[j + s*T] --------
-        float t[32];
-        tmem_ld32(ta + C::TM_TW3, t);     // entry b*(R3-1) + k-1
-#pragma unroll
-        for (int b = 0; b < NB3; b++) {
-          float2 v[R3];
-#pragma unroll
-          for (int k = 0; k < R3; k++) v[k] = x[b + k * NB3];
-#pragma unroll
-          for (int k = 1; k < R3; k++) {
-            const int e = b * (R3 - 1) + k - 1;
-            v[k] = cmul(v[k], make_float2(t[2 * e], t[2 * e + 1]));
-          }
-          dft<R3>(v);
-#pragma unroll
-          for (int k = 0; k < R3; k++) x[b + k * NB3] = v[k];
-        }
       }
 
-      // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
-      // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
-      {
-        // both sides of this exchange are unit-stride across lanes: no padding needed
-        float2 *w = wbuf + j;
+      if constexpr (MIRG) {
+        // ---- last pass: LNB butterflies of radix LR, x[b*LR + q] = Z[butterfly_b + q*LS] afterwards --------
+        {
+          float t[32];
+          if constexpr (C::FOUR) {
+            float t4[16];
+            tmem_ld16(ta + C::TM_TW4, t4);
 #pragma unroll
-        for (int s = E / 2; s < E; s++) w[(s - E / 2) * T] = x[s];
-      }
-      group_sync<T>(g);
-      {
-        // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
-        const float2 *r = wbuf + (M / 2 - j);
+            for (int e = 0; e < 16; e++) t[e] = t4[e];
+          } else {
+            tmem_ld32(ta + C::TM_TW3, t);   // entry b*(LR-1) + k-1
+          }
+#pragma unroll
+          for (int b = 0; b < LNB; b++) {
+            float2 v[LR];
+#pragma unroll
+            for (int k = 0; k < LR; k++) v[k] = x[b * LR + k];
+#pragma unroll
+            for (int k = 1; k < LR; k++) {
+              const int e = b * (LR - 1) + k - 1;
+              v[k] = cmul(v[k], make_float2(t[2 * e], t[2 * e + 1]));
+            }
+            dft<LR>(v);
+#pragma unroll
+            for (int k = 0; k < LR; k++) x[b * LR + k] = v[k];
+          }
+        }
+        // ---- recombination in registers (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ----
         float tr[16];
-        tmem_ld16(ta + C::TM_TWR, tr);
-#pragma unroll
-        for (int s = 0; s < E / 2; s++) {
-          const float2 a = x[s];
-          const float2 bq = r[-s * T];
-          const float2 w = make_float2(tr[2 * s], tr[2 * s + 1]);
+        tmem_ld16(ta + C::TM_TWR, tr);     // W_N^k in the order of the pairs below
+        auto pair_mag = [&](float2 a, float2 bq, float2 w, float &m0, float &m1) {
           // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
           const float2 cb = make_float2(bq.x, -bq.y);
           const float2 pp = add2(a, cb), qq = sub2(a, cb);
           const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
           const float2 uu = add2(pp, tt), vv = sub2(pp, tt);
-          val[2 * s] = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
-          val[2 * s + 1] = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
+          m0 = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
+          m1 = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
+        };
+#pragma unroll
+        for (int i = 0; i < LH; i++) {
+          const float2 *oa = x + (2 * i) * LR, *ob = x + (2 * i + 1) * LR;
+          const bool t0s = (i == 0) && (j == 0);   // thread 0: A_0 = 0 pairs with itself, B_0 = S/2 with itself
+#pragma unroll
+          for (int q = 0; q < LR / 2; q++) {
+            const int pidx = i * LR + 2 * q;
+            // k = A_i + q*LS pairs with M - k = B_i + (LR-1-q)*LS
+            const float2 p1 = t0s ? oa[(LR - q) & (LR - 1)] : ob[LR - 1 - q];
+            pair_mag(oa[q], p1, make_float2(tr[2 * pidx], tr[2 * pidx + 1]), val[2 * pidx], val[2 * pidx + 1]);
+            // k = B_i + q*LS pairs with M - k = A_i + (LR-1-q)*LS
+            const float2 p2 = t0s ? ob[LR - 1 - q] : oa[LR - 1 - q];
+            pair_mag(ob[q], p2, make_float2(tr[2 * pidx + 2], tr[2 * pidx + 3]), val[2 * pidx + 2], val[2 * pidx + 3]);
+          }
         }
         if (j == 0) {
-          // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
-          const float2 z0 = x[0];
-          const float2 zm = wbuf[0];
-          val[0] = 2.0f * fabsf(z0.x + z0.y);                      // X[0]   = Zr + Zi
-          val[1] = 2.0f * fabsf(z0.x - z0.y);                      // X[N/2] = Zr - Zi (packed Nyquist)
-          vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
+          const float2 z0 = x[0], zm = x[LR / 2];                    // Z[0] and Z[(LR/2)*LS] = Z[M/2]
+          val[0] = 2.0f * fabsf(z0.x + z0.y);                        // X[0]   = Zr + Zi
+          val[1] = 2.0f * fabsf(z0.x - z0.y);                        // X[N/2] = Zr - Zi (packed Nyquist)
+          vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y));  // X[N/4] = conj(Z[M/2])
         }
+      } else {
+        // ---- N = 8192: pass 3 (last), one radix-16 butterfly per thread: x[s] = Z[j + s*T] -------------
+        {
+          float t[32];
+          tmem_ld32(ta + C::TM_TW3, t);     // entry k-1
+#pragma unroll
+          for (int k = 1; k < R3; k++) x[k] = cmul(x[k], make_float2(t[2 * (k - 1)], t[2 * (k - 1) + 1]));
+          dft<R3>(x);
+        }
+        // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
+        // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
+        {
+          // both sides of this exchange are unit-stride across lanes: no padding needed
+          float2 *w = wbuf + j;
+#pragma unroll
+          for (int s = E / 2; s < E; s++) w[(s - E / 2) * T] = x[s];
+        }
+        group_sync<T>(g);
+        {
+          // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
+          const float2 *r = wbuf + (M / 2 - j);
+          float tr[16];
+          tmem_ld16(ta + C::TM_TWR, tr);
+#pragma unroll
+          for (int s = 0; s < E / 2; s++) {
+            const float2 a = x[s];
+            const float2 bq = r[-s * T];
+            const float2 w = make_float2(tr[2 * s], tr[2 * s + 1]);
+            // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
+            const float2 cb = make_float2(bq.x, -bq.y);
+            const float2 pp = add2(a, cb), qq = sub2(a, cb);
+            const float2 tt = fma2(bcast2(w.x), make_float2(qq.y, -qq.x), mul2(bcast2(w.y), qq));
+            const float2 uu = add2(pp, tt), vv = sub2(pp, tt);
+            val[2 * s] = sqrt_approx(fmaf(uu.x, uu.x, uu.y * uu.y));
+            val[2 * s + 1] = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
+          }
+          if (j == 0) {
+            // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
+            const float2 z0 = x[0];
+            const float2 zm = wbuf[0];
+            val[0] = 2.0f * fabsf(z0.x + z0.y);                      // X[0]   = Zr + Zi
+            val[1] = 2.0f * fabsf(z0.x - z0.y);                      // X[N/2] = Zr - Zi (packed Nyquist)
+            vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
+          }
+        }
+        { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
       }
-      { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
     }
     // bin index of val[i]
     auto binof = [&](int i) -> uint32_t {
@@ -587,6 +652,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         const int q = i >> 2, r = i & 3;
         const uint32_t k = (uint32_t)(((r & 2) ? jbB : j) + 256 * q);
         return (r & 1) ? (uint32_t)M - k : k;
+      } else if constexpr (MIRG) {
+        const int pidx = i >> 1, sl = pidx / LR, rem = pidx % LR;
+        const uint32_t k = (uint32_t)(((rem & 1) ? bfB(sl) : bfA(sl)) + (rem >> 1) * LS);
+        return (i & 1) ? (uint32_t)M - k : k;
       } else {
         const uint32_t k = (uint32_t)(j + (i >> 1) * T);
         return (i & 1) ? (uint32_t)M - k : k;
