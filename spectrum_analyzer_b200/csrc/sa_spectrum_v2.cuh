@@ -85,9 +85,9 @@ struct V2Cfg {
   static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
   // the per-thread constants (window multipliers, pass twiddles, recombination
   // twiddles: 112 words per thread) in tensor memory, read with tcgen05.ld (sa_tmem.cuh): column
-  // layout [0,32) window | [32,62) pass-2 twiddles | [64,94) last-pass twiddles | [96,112) recombination.
+  // layout [0,32) window | [32,62) pass-2 twiddles | [64,94) pass-3 twiddles | [96,112) recombination |
+  // [112,128) pass-4 twiddles (N = 16384).
   // A thread's lane is 32*(warp%4)+lane_id; groups wider than 128 threads use T/128 column sets.
-  // (the fourth-pass twiddles of N = 16384 stay in global memory)
   // Warp roles are rotated from group to group (thread 0 of a group does extra work -- the record, bin
   // M/2 -- and would otherwise always sit on the same SM sub-partition): group g's logical warp w is
   // physical warp (w - rot(g)) mod NW, rot(g) = (g / GPQ) % NROT.  One table copy per rotation.
