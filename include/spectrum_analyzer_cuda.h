@@ -114,6 +114,12 @@ int sa_ctx_create(int device, sa_ctx **out_ctx);
 int sa_ctx_create_on_stream(int device, void *cuda_stream, sa_ctx **out_ctx);
 int sa_ctx_destroy(sa_ctx *ctx);
 int sa_ctx_sync(sa_ctx *ctx);
+
+/* Opt-in (default off): the fused 20*log10 scaling of the tuned kernels (n >= 64, suitably aligned input) uses
+ * the hardware log2 approximation instead of the libm `log10f` operation sequence.  Values differ from
+ * `20.0 * libm::log10f(v)` (src/scaling.rs:104-114) by a few ulp of the f32 dB value (measured <= 4; lg2.approx has a relative error of about 2^-22)
+ * and are no longer bit-exact functions of the magnitude; 1.5x-1.7x faster in that mode.  The statistics stay exact order statistics of the values written. */
+int sa_ctx_set_fast_log10(sa_ctx *ctx, int enable);
 /* Number of kernels this context has launched so far (for bench accounting). */
 uint64_t sa_ctx_launch_count(const sa_ctx *ctx);
 

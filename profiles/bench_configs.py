@@ -48,11 +48,17 @@ def main():
         ("512 hann all none", 512, 512, 8 * 1024 * 1024, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
         ("32768 hann all none", 32768, 32768, 65_536, cabi.WINDOW_HANN, L.All, cabi.SCALING_NONE, 7),
         ("2048 hamming hop441 (odd hop: frames on 4-byte boundaries)", 2048, 441, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
+        ("fastlog cfg5 256 log10 median (sa_ctx_set_fast_log10)", 256, 256, 16 * 1024 * 1024, cabi.WINDOW_NONE, L.All,
+         cabi.SCALING_20_TIMES_LOG10, 7),
+        ("4096 hann all log10", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All, cabi.SCALING_20_TIMES_LOG10, 7),
+        ("fastlog 4096 hann all log10 (sa_ctx_set_fast_log10)", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All,
+         cabi.SCALING_20_TIMES_LOG10, 7),
         ("i16 cfg2 4096 hann all div_sqrt", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All, cabi.SCALING_DIVIDE_BY_N_SQRT, 7),
         ("i16 cfg3 2048 hamming hop512", 2048, 512, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
     ]
     for name, n, hop, frames, win, lim, sc, st in configs:
         i16 = name.startswith("i16")
+        chk(lib.sa_ctx_set_fast_log10(ctx._h, 1 if name.startswith("fastlog") else 0))
         frames = max(1024, int(frames * args.scale))
         nsamp = (frames - 1) * hop + n
         x = torch.empty(nsamp, dtype=torch.float32, device=dev)

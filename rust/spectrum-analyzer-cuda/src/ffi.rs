@@ -32,6 +32,7 @@ extern "C" {
     pub fn sa_ctx_create_on_stream(device: c_int, cuda_stream: *mut c_void, out_ctx: *mut *mut sa_ctx) -> c_int;
     pub fn sa_ctx_destroy(ctx: *mut sa_ctx) -> c_int;
     pub fn sa_ctx_sync(ctx: *mut sa_ctx) -> c_int;
+    pub fn sa_ctx_set_fast_log10(ctx: *mut sa_ctx, enable: c_int) -> c_int;
     pub fn sa_ctx_launch_count(ctx: *const sa_ctx) -> u64;
     pub fn sa_window_coeffs(window_kind: c_int, n: u32, host_out: *mut f32) -> c_int;
     pub fn sa_limit_to_bins(n: u32, sampling_rate: u32, limit_kind: c_int, limit_lo: f32, limit_hi: f32,

@@ -186,6 +186,11 @@ class Context:
     def sync(self):
         _check(A.load().sa_ctx_sync(self._h))
 
+    def set_fast_log10(self, enable: bool = True) -> None:
+        """Opt-in: fused ``scale_20_times_log10`` through the hardware log2 approximation (within 4 ulp of the
+        libm sequence's f32 dB value, 1.5-1.7x faster in that mode).  Default off."""
+        _check(A.load().sa_ctx_set_fast_log10(self._h, 1 if enable else 0))
+
     @property
     def launch_count(self) -> int:
         return int(A.load().sa_ctx_launch_count(self._h))

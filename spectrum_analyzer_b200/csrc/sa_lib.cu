@@ -58,6 +58,7 @@ struct sa_ctx {
   uint64_t launches = 0;
   bool use_generic = false;   // SA_FORCE_GENERIC=1: run the generic kernel family for every N (A/B testing)
   unsigned stagger_ns = 1000; // SA_STAGGER_NS: start offset between the frame groups of a v2 CTA (tuning)
+  bool fast_log10 = false;    // sa_ctx_set_fast_log10
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
   KernelPlan plans[16];                                     // per log2n (generic family)
@@ -344,6 +345,7 @@ int fill_params(sa_ctx *ctx, SpectrumParams &p, const void *d_samples, int in_i1
   if ((e = get_window(ctx, window_kind, n, &p.window)) != SA_OK) return e;
   p.samples = static_cast<const float *>(d_samples);
   p.in_i16 = in_i16;
+  p.fast_log10 = ctx->fast_log10 ? 1 : 0;
   p.out_vals = d_out;
   p.stats = (stats_mask & SA_STATS_ALL) ? d_stats : nullptr;
   p.n_frames = n_frames;
@@ -498,6 +500,12 @@ int sa_ctx_destroy(sa_ctx *ctx) {
   if (ctx->single_dev) cudaFree(ctx->single_dev);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return SA_OK;
+}
+
+int sa_ctx_set_fast_log10(sa_ctx *ctx, int enable) {
+  if (!ctx) return SA_ERR_INVALID_ARGUMENT;
+  ctx->fast_log10 = enable != 0;
   return SA_OK;
 }
 

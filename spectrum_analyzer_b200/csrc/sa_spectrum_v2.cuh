@@ -719,6 +719,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
       for (int i = 0; i < E; i++) val[i] = div_by_frame_max(val[i], umax, rmax);
       vmid = div_by_frame_max(vmid, umax, rmax);
+    } else if (MODE == SCALE_LOG10 && p.fast_log10) {   // launch-uniform opt-in
+#pragma unroll
+      for (int i = 0; i < E; i++) val[i] = (val[i] == 0.0f) ? 0.0f : db_fast(val[i]);
+      vmid = (vmid == 0.0f) ? 0.0f : db_fast(vmid);
     } else {
 #pragma unroll
       for (int i = 0; i < E; i++) val[i] = scale1(val[i]);

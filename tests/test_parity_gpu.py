@@ -359,3 +359,38 @@ def test_repeat_launch_is_bit_identical(gpu_ctx, n):
         runs.append((r.vals.view(torch.int32).clone(), r.stats.clone()))
     for v, s in runs[1:]:
         assert torch.equal(v, runs[0][0]) and torch.equal(s, runs[0][1])
+
+
+@pytest.mark.parametrize("n", [256, 4096])
+def test_fast_log10_option(gpu_ctx, n):
+    """sa_ctx_set_fast_log10 (opt-in): dB values through lg2.approx stay within 4 ulp of the exact libm
+    sequence (src/scaling.rs:104-114), zeros stay zeros, and the statistics are still exact order statistics
+    of the values written.  The default (off) is untouched."""
+    import torch
+    m = sa()
+    frames = 64
+    x = torch.from_numpy(noise(frames, n, seed=99, amp=1000.0)).cuda()
+    x[: n] = 0.0                                                         # an all-zero frame: every dB value is 0
+    kw = dict(window=O.WINDOW_HANN, n=n, frame_stride=n, n_frames=frames, stats=7)
+    exact = m.samples_fft_to_spectrum_batched(x, 44100, m.FrequencyLimit.All, m.scaling.scale_20_times_log10, **kw)
+    torch.cuda.synchronize()
+    ctx = m.Context(0, torch.cuda.current_stream().cuda_stream)
+    ctx.set_fast_log10(True)
+    fast = m.samples_fft_to_spectrum_batched(x, 44100, m.FrequencyLimit.All, m.scaling.scale_20_times_log10, ctx=ctx, **kw)
+    torch.cuda.synchronize()
+    ev, fv = exact.vals.cpu().numpy(), fast.vals.cpu().numpy()
+    assert np.all(fv[0] == 0.0) and np.all(ev[0] == 0.0)
+    # lg2.approx carries a relative error of about 2^-22; both results are then rounded to f32
+    # (ulp of an 80 dB value: 7.6e-6 dB)
+    err = np.abs(ev - fv) / (np.spacing(np.abs(ev)) + 1e-6)
+    assert err.max() <= 4.0, f"fast log10 off by {err.max():.2f} ulp"
+    assert not np.array_equal(ev, fv)                                    # it really is another code path
+    fs = fast.stats_numpy()
+    for f in range(0, frames, 7):
+        s = O.calc_statistics(fv[f])
+        assert (s.min_val, s.min_bin, s.max_val, s.max_bin, s.median) == \
+            (fs["min_val"][f], fs["min_bin"][f], fs["max_val"][f], fs["max_bin"][f], fs["median"][f])
+    ctx.set_fast_log10(False)
+    again = m.samples_fft_to_spectrum_batched(x, 44100, m.FrequencyLimit.All, m.scaling.scale_20_times_log10, ctx=ctx, **kw)
+    torch.cuda.synchronize()
+    assert np.array_equal(again.vals.cpu().numpy(), ev)
