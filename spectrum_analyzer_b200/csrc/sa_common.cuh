@@ -114,6 +114,49 @@ __device__ __forceinline__ float log10f_musl(float x) {
   return r;
 }
 
+// The same sequence for positive NORMAL finite x only (every magnitude the tuned kernels produce through
+// sqrt.approx.ftz: >= 1e-19 or exactly 0, which the caller maps to 0 as src/scaling.rs:108-112 does).  Bit-identical
+// to log10f_musl on that domain with fewer instructions and no branch:
+//  * no subnormal rescaling;
+//  * no early return for x == 1: the general path yields +0 there (f = 0 => every term is +-0, the sum +0);
+//  * s = f / (2 + f) by rcp.approx + one Newton step + two FMA corrections of the quotient instead of the IEEE
+//    division routine -- equal to __fdiv_rn for ALL 2^23 possible (f, 2+f) of this call site, checked
+//    exhaustively by profiles/microbench/log10_div_check.cu.
+__device__ __forceinline__ float log10f_musl_normal(float x) {
+  const float ivln10hi = 4.3432617188e-01f, ivln10lo = -3.1689971365e-05f,
+              log10_2hi = 3.0102920532e-01f, log10_2lo = 7.9034151668e-07f,
+              Lg1 = 0xaaaaaa.0p-24f, Lg2 = 0xccce13.0p-25f, Lg3 = 0x91e9ee.0p-25f, Lg4 = 0xf89e26.0p-26f;
+  uint32_t ix = __float_as_uint(x);
+  ix += 0x3f800000u - 0x3f3504f3u;
+  const int k = (int)(ix >> 23) - 0x7f;
+  ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+  x = __uint_as_float(ix);
+  const float f = __fsub_rn(x, 1.0f);
+  const float d = __fadd_rn(2.0f, f);
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+  y = __fmaf_rn(y, __fmaf_rn(-d, y, 1.0f), y);
+  float s = __fmul_rn(f, y);
+  s = __fmaf_rn(__fmaf_rn(-s, d, f), y, s);
+  s = __fmaf_rn(__fmaf_rn(-s, d, f), y, s);
+  const float z = __fmul_rn(s, s);
+  const float w = __fmul_rn(z, z);
+  const float t1 = __fmul_rn(w, __fadd_rn(Lg2, __fmul_rn(w, Lg4)));
+  const float t2 = __fmul_rn(z, __fadd_rn(Lg1, __fmul_rn(w, Lg3)));
+  const float R = __fadd_rn(t2, t1);
+  const float hfsq = __fmul_rn(__fmul_rn(0.5f, f), f);
+  float hi = __fsub_rn(f, hfsq);
+  hi = __uint_as_float(__float_as_uint(hi) & 0xfffff000u);
+  const float lo = __fadd_rn(__fsub_rn(__fsub_rn(f, hi), hfsq), __fmul_rn(s, __fadd_rn(hfsq, R)));
+  const float dk = (float)k;
+  float r = __fmul_rn(dk, log10_2lo);
+  r = __fadd_rn(r, __fmul_rn(__fadd_rn(lo, hi), ivln10lo));
+  r = __fadd_rn(r, __fmul_rn(lo, ivln10hi));
+  r = __fadd_rn(r, __fmul_rn(hi, ivln10hi));
+  r = __fadd_rn(r, __fmul_rn(dk, log10_2hi));
+  return r;
+}
+
 // v: unscaled magnitude; div: stats.n or sqrtf(stats.n); vmax: pre-scaling maximum.
 __device__ __forceinline__ float apply_scaling(int kind, float v, float div, float vmax) {
   switch (kind) {

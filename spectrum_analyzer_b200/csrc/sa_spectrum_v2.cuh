@@ -723,6 +723,14 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
       for (int i = 0; i < E; i++) val[i] = (val[i] == 0.0f) ? 0.0f : db_fast(val[i]);
       vmid = (vmid == 0.0f) ? 0.0f : db_fast(vmid);
+    } else if constexpr (MODE == SCALE_LOG10) {
+      // bins 0 and N/2 of thread 0 are |Zr +- Zi| (they may be subnormal): full libm sequence; every other value
+      // comes out of sqrt.approx.ftz (normal or exactly zero): the branch-free variant, same bits
+      const float dc0 = val[0], dc1 = val[1];
+#pragma unroll
+      for (int i = 0; i < E; i++) val[i] = (val[i] == 0.0f) ? 0.0f : __fmul_rn(20.0f, log10f_musl_normal(val[i]));
+      vmid = (vmid == 0.0f) ? 0.0f : __fmul_rn(20.0f, log10f_musl_normal(vmid));
+      if (j == 0) { val[0] = scale1(dc0); val[1] = scale1(dc1); }
     } else {
 #pragma unroll
       for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
