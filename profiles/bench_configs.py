@@ -53,6 +53,10 @@ def main():
         ("4096 hann all log10", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All, cabi.SCALING_20_TIMES_LOG10, 7),
         ("fastlog 4096 hann all log10 (sa_ctx_set_fast_log10)", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All,
          cabi.SCALING_20_TIMES_LOG10, 7),
+        ("4096 hann max(4000) div_sqrt (372 of 2049 bins kept)", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.Max(4000.0),
+         cabi.SCALING_DIVIDE_BY_N_SQRT, 7),
+        ("4096 hann range(50,12000) div_sqrt (1111 bins kept)", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.Range(50.0, 12000.0),
+         cabi.SCALING_DIVIDE_BY_N_SQRT, 7),
         ("i16 cfg2 4096 hann all div_sqrt", 4096, 4096, 1_000_000, cabi.WINDOW_HANN, L.All, cabi.SCALING_DIVIDE_BY_N_SQRT, 7),
         ("i16 cfg3 2048 hamming hop512", 2048, 512, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
     ]
