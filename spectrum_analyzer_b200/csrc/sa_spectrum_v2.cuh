@@ -770,14 +770,20 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           kmx = max(kmx, max(k0, k1));
         }
       } else {
+        // FrequencyLimit slices: min / max / sum under the per-bin predicate; then the dropped bins are replaced
+        // by +Inf (its key lies above every finite key in all modes) so that the histogram atomics below stay
+        // unconditional like in the All case (a predicated shared-memory atomic becomes a branch): +Inf lands in
+        // the "above" slot, which no rank looks at; every later use of a dropped bin is still predicated.
 #pragma unroll
         for (int i = 0; i < E; i++) {
-          if (SA_VALID(i)) {
+          const bool keep = SA_VALID(i);
+          if (keep) {
             const uint32_t k = v2_key<MODE>(val[i]);
             kmn = min(kmn, k);
             kmx = max(kmx, k);
             sum += val[i];
           }
+          val[i] = keep ? val[i] : __uint_as_float(0x7f800000u);
         }
       }
       if (valid_mid) {
@@ -788,8 +794,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
       if (use_win) {
 #pragma unroll
-        for (int i = 0; i < E; i++)
-          if (SA_VALID(i)) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(val[i]), winL, shw)], 1u);
+        for (int i = 0; i < E; i++)   // unconditional: dropped bins are +Inf and count as "above"
+          atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(val[i]), winL, shw)], 1u);
         if (valid_mid) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(vmid), winL, shw)], 1u);
       }
       const uint32_t my_kmn = kmn, my_kmx = kmx;
