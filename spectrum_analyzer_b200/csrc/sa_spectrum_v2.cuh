@@ -19,8 +19,9 @@
 //    phase, which then waits for DRAM.  Frames that do not start on a 16-byte boundary are copied as
 //    their aligned superset and read at an offset, so any hop / base alignment takes this family.
 //  * two exchange buffers per group, alternated on every exchange: one barrier per exchange (one-warp
-//    groups, N = 1024, reuse a single buffer between __syncwarp()s); every size but N = 8192 pairs
-//    mirrored last-pass butterflies in one thread so the real-FFT recombination needs no exchange.
+//    groups, N = 1024, reuse a single buffer between __syncwarp()s); mirrored last-pass butterflies
+//    meet in one thread (N = 8192: in two lanes of one warp), so the real-FFT recombination needs no
+//    shared-memory exchange.
 //  * magnitude = sqrt.approx(|.|^2) * c, where c folds the real-FFT 1/2 and a power-of-two scaling
 //    divisor (divide_by_N always, divide_by_N_sqrt when log2 N is even) into one exact multiply;
 //    other divisors use an exactly-rounded FMA division.
@@ -200,7 +201,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // radix-2 fourth pass of N = 16384): with S = (butterflies of the last pass) = LNB*T, thread j owns the LNB/2
   // butterflies A_i = j + i*T and their mirrors B_i = S - A_i (thread 0: B_0 = S/2, the self-mirrored one, and
   // A_0 = 0 pairs with itself), so every pair Z[k], Z[M-k] meets in one thread and the recombination needs no
-  // exchange.  N = 8192 (one radix-16 butterfly per thread) keeps the exchange.
+  // exchange.  N = 8192 runs ONE radix-16 butterfly per thread: there the butterflies are dealt so that lane l < 16
+  // of (logical) warp w owns butterfly 16w + l and lane l + 16 its mirror 256 - (16w + l) (warp 0: lane 16 owns the
+  // self-mirrored 128), and the partner's outputs arrive by 16 shuffles (xor 16) instead of a shared-memory
+  // exchange and a barrier.
   constexpr int LR = C::FOUR ? C::R4 : R3, LNB = C::FOUR ? C::NB4 : NB3, LS = LNB * T, LH = LNB / 2;
   constexpr bool MIRG = !MIRROR && LNB >= 2;
 
@@ -243,6 +247,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
   const int jbB = j ? 256 - j : 128;   // MIRROR: second last-pass butterfly of this thread
+  // N = 8192 (neither MIRROR nor MIRG): butterfly of this thread in the last pass
+  const int beta = (j & 31) < 16 ? 16 * (j >> 5) + (j & 31)
+                                 : (j == 16 ? 128 : 256 - (16 * (j >> 5) + (j & 31) - 16));
   auto bfA = [&](int i) -> int { return j + i * T; };                                         // MIRG
   auto bfB = [&](int i) -> int { return j ? LS - (j + i * T) : (i ? LS - i * T : LS / 2); };  // MIRG
   const uint32_t ta = tmem_addr(tm_base, tid >> 5, (rot * C::TM_JSETS + (j >> 7)) * C::TM_SET_COLS);   // this thread's table row
@@ -277,7 +284,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           float2 w = make_float2(0.f, 0.f);
           if (e < NB3 * (R3 - 1)) {
             const int b = e / (R3 - 1), k = e % (R3 - 1) + 1;
-            const int jb = MIRROR ? (b ? jbB : j) : C::FOUR ? (j & 255) : MIRG ? ((b & 1) ? bfB(b >> 1) : bfA(b >> 1)) : j + b * T;
+            const int jb = MIRROR ? (b ? jbB : j) : C::FOUR ? (j & 255) : MIRG ? ((b & 1) ? bfB(b >> 1) : bfA(b >> 1)) : beta;
             w = __ldg(P.tw3 + (k - 1) * 256 + jb);
           }
           v[2 * s] = w.x; v[2 * s + 1] = w.y;
@@ -286,7 +293,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
 #pragma unroll
       for (int s = 0; s < 8; s++) {   // recombination twiddles W_N^k of the 8 bin pairs this thread owns
-        int k = MIRROR ? ((s & 1) ? jbB : j) + 256 * (s >> 1) : j + s * T;
+        int k = MIRROR ? ((s & 1) ? jbB : j) + 256 * (s >> 1) : beta + s * 256;
         if constexpr (MIRG) { const int i = s / LR, rem = s % LR; k = ((rem & 1) ? bfB(i) : bfA(i)) + (rem >> 1) * LS; }
         const float2 w = __ldg(P.twr + k);
         v[2 * s] = w.x; v[2 * s + 1] = w.y;
@@ -513,7 +520,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       if constexpr (MIRG && !C::FOUR) {
         read_mirror_list();
       } else {
-        const float2 *r = wbuf + j;
+        const float2 *r = wbuf + (C::FOUR ? j : beta);   // N = 8192: inputs of butterfly beta (T = 256 = stride)
 #pragma unroll
         for (int s = 0; s < 16; s++) x[s] = r[s * T];
       }
@@ -608,23 +615,20 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           dft<R3>(x);
         }
         // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ------
-        // upper half Z[M/2 .. M) goes through shared memory; thread j pairs k = j + s*T with M - k.
+        // k = beta + 256 s pairs with M - k = (256 - beta) + 256 (15 - s): output 15 - s of the partner lane
+        static_assert(T == 256 && R3 == 16, "shuffle-mirrored last pass is written for N = 8192");
         {
-          // both sides of this exchange are unit-stride across lanes: no padding needed
-          float2 *w = wbuf + j;
-#pragma unroll
-          for (int s = E / 2; s < E; s++) w[(s - E / 2) * T] = x[s];
-        }
-        group_sync<T>(g);
-        {
-          // partner of k = j + s*T sits at index M/2 - k of the (unpadded) upper-half buffer
-          const float2 *r = wbuf + (M / 2 - j);
           float tr[16];
           tmem_ld16(ta + C::TM_TWR, tr);
+          const bool self0 = (beta == 0), self128 = (beta == 128);   // butterflies that pair with themselves
 #pragma unroll
           for (int s = 0; s < E / 2; s++) {
             const float2 a = x[s];
-            const float2 bq = r[-s * T];
+            float2 bq;
+            bq.x = __shfl_xor_sync(0xffffffffu, x[15 - s].x, 16);
+            bq.y = __shfl_xor_sync(0xffffffffu, x[15 - s].y, 16);
+            if (self128) bq = x[15 - s];
+            if (self0) bq = x[(16 - s) & 15];
             const float2 w = make_float2(tr[2 * s], tr[2 * s + 1]);
             // P = A + conj(B), Q = A - conj(B), T = -i w Q (w = (cos,-sin)), 2X[k] = P + T, 2conj(X[M-k]) = P - T
             const float2 cb = make_float2(bq.x, -bq.y);
@@ -635,15 +639,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
             val[2 * s + 1] = sqrt_approx(fmaf(vv.x, vv.x, vv.y * vv.y));
           }
           if (j == 0) {
-            // (j,s)=(0,0): the generic pair above read Z[M/2] as its partner; redo bins 0 / M / M/2 exactly
-            const float2 z0 = x[0];
-            const float2 zm = wbuf[0];
+            const float2 z0 = x[0], zm = x[8];                        // Z[0] and Z[8*256] = Z[M/2]
             val[0] = 2.0f * fabsf(z0.x + z0.y);                      // X[0]   = Zr + Zi
             val[1] = 2.0f * fabsf(z0.x - z0.y);                      // X[N/2] = Zr - Zi (packed Nyquist)
             vmid = 2.0f * sqrt_approx(fmaf(zm.x, zm.x, zm.y * zm.y)); // X[N/4] = conj(Z[M/2])
           }
         }
-        { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
       }
     }
     // bin index of val[i]
@@ -657,7 +658,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         const uint32_t k = (uint32_t)(((rem & 1) ? bfB(sl) : bfA(sl)) + (rem >> 1) * LS);
         return (i & 1) ? (uint32_t)M - k : k;
       } else {
-        const uint32_t k = (uint32_t)(j + (i >> 1) * T);
+        const uint32_t k = (uint32_t)(beta + (i >> 1) * 256);
         return (i & 1) ? (uint32_t)M - k : k;
       }
     };
