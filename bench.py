@@ -168,6 +168,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -346,6 +347,7 @@ def run_ours(args):
                                    "FrequencyLimit::All (BASELINE.json configs[1])",
                        "frames_per_gpu": frames, "n": N, "n_bins": N_BINS, "out_stride": out_stride,
                        "stats_mask": stats_mask, "sharding": f"contiguous frame ranges, {world} rank(s), no collective",
+                       "host_numa_node_rank0": numa,
                        "l2": "inputs (16.4 GB/GPU) and outputs (8.2 GB/GPU) are far larger than the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -356,6 +358,28 @@ def run_ours(args):
 
 
 _JSON_OUT = None
+
+
+def bind_to_gpu_numa_node(torch, local_rank: int):
+    """Best effort, multi-rank runs only: run this rank on the CPUs next to its GPU so that the pinned host
+    buffers of the end-to-end measurement are allocated on that NUMA node (first touch) and the PCIe traffic
+    does not cross sockets.  Returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def emit(line: dict) -> None:
