@@ -57,7 +57,7 @@ struct sa_ctx {
   bool owns_stream = false;
   uint64_t launches = 0;
   bool use_generic = false;   // SA_FORCE_GENERIC=1: run the generic kernel family for every N (A/B testing)
-  unsigned stagger_ns = 1000; // SA_STAGGER_NS: start offset between the frame groups of a v2 CTA (tuning)
+  unsigned stagger_ns = 0;    // SA_STAGGER_NS: start offset between the frame groups of a v2 CTA (tuning; measured: no effect)
   bool fast_log10 = false;    // sa_ctx_set_fast_log10
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
