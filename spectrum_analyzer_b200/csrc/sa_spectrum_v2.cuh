@@ -135,8 +135,8 @@ __device__ __forceinline__ uint32_t hist_slot(uint32_t k, uint32_t klo, int sh) 
     return k < klo ? 0u : d;
   } else {
     // keys are bit patterns of non-negative floats (< 2^31): the signed difference cannot overflow
-    const int d = (int)(k - klo) >> sh;      // arithmetic shift: negative when k < klo
-    return (uint32_t)(max(min(d, NB), -1) + 1);
+    const int d1 = ((int)(k - klo) >> sh) + 1;      // arithmetic shift: negative when k < klo
+    return (uint32_t)__vimin_s32_relu(d1, NB + 1);   // one instruction: max(min(d1, NB + 1), 0)
   }
 }
 
