@@ -114,8 +114,14 @@ struct V2Cfg {
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
   // the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
-  static constexpr size_t G_STAGE = sizeof(float) * N + 32;   // samples (+16 B of alignment slack) + mbarrier
-  static constexpr size_t G_BYTES = NBUF * G_BUF + G_HIST + G_MISC + G_LIST + G_STAGE;
+  // N = 4096: the staged frame lives in the second exchange buffer (free between the last-pass reads of one frame
+  // and the second exchange of the next), so a group needs 37 KB instead of 54 KB and five or six groups fit on
+  // an SM (94 / 80 registers per thread; five measured best); the copy is issued after the statistics barrier
+  // instead of after the first one
+  static constexpr bool ALIAS = (NB3 == 2);
+  static constexpr size_t G_BUFB = ALIAS ? sizeof(float2) * M + 32 : G_BUF;   // ALIAS: unpadded exchange / frame + slack
+  static constexpr size_t G_STAGE = ALIAS ? 16 : sizeof(float) * N + 32;      // samples (+16 B of alignment slack) + mbarrier
+  static constexpr size_t G_BYTES = G_BUF + (NBUF - 1) * G_BUFB + G_HIST + G_MISC + G_LIST + G_STAGE;
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
 };
 
@@ -217,11 +223,14 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   unsigned char *gbase = smem + C::OFF_GROUPS + (size_t)g * C::G_BYTES;
   float2 *bufA = reinterpret_cast<float2 *>(gbase);
   float2 *bufB = reinterpret_cast<float2 *>(gbase + (C::NBUF - 1) * C::G_BUF);   // == bufA when NBUF == 1
-  uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + C::NBUF * C::G_BUF);
-  uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + C::NBUF * C::G_BUF + C::G_HIST);
-  uint32_t *list = reinterpret_cast<uint32_t *>(gbase + C::NBUF * C::G_BUF + C::G_HIST + C::G_MISC);
-  unsigned char *stage = gbase + C::NBUF * C::G_BUF + C::G_HIST + C::G_MISC + C::G_LIST;
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(stage + sizeof(float) * N + 16);
+  constexpr size_t OFF_HIST = C::G_BUF + (C::NBUF - 1) * C::G_BUFB;
+  uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + OFF_HIST);
+  uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + OFF_HIST + C::G_HIST);
+  uint32_t *list = reinterpret_cast<uint32_t *>(gbase + OFF_HIST + C::G_HIST + C::G_MISC);
+  unsigned char *tail = gbase + OFF_HIST + C::G_HIST + C::G_MISC + C::G_LIST;
+  constexpr bool ALIAS = C::ALIAS;
+  unsigned char *stage = ALIAS ? reinterpret_cast<unsigned char *>(bufB) : tail;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(ALIAS ? tail : tail + sizeof(float) * N + 16);
   uint32_t phase = 0;              // parity of the mbarrier phase the next wait completes
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
 #ifndef SA_GW_MIN_LOG2
@@ -434,7 +443,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
     group_sync<T>(g);
     // every thread of the group has consumed the staged samples and finished the previous frame
-    if (j == 0 && more) stage_frame(frame + fstep);
+    if constexpr (!ALIAS) { if (j == 0 && more) stage_frame(frame + fstep); }
     if (want_stats && rec_thread) flush_record();
     {
       const float2 *r = wbuf + (j + (j >> 4));
@@ -739,6 +748,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
     if constexpr (MODE == SCALE_MUL) vmid = scale1(vmid);
 
+    if constexpr (ALIAS) {
+      if (!want_stats) {   // no statistics barrier to hang the copy on: one extra group barrier
+        group_sync<T>(g);
+        if (j == 0 && more) stage_frame(frame);
+      }
+    }
     // ---- statistics of the scaled values (src/spectrum.rs:481-539) --------------------------------
     if (want_stats) {
       // layout of one histogram (HSTRIDE words): [3 pad | below | NBUCKET buckets (16-byte aligned) | above | pad]
@@ -811,6 +826,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       if constexpr (NW > 1 && !(SA_EXP & 4)) {
         if (lane == 0) { misc[MI_KMIN + wig] = kmn; misc[MI_KMAX + wig] = kmx; misc[MI_SUM + wig] = __float_as_uint(sum); }
         group_sync<T>(g);
+        // every thread has read its last-pass inputs from the second exchange buffer: the next frame may land there
+        if constexpr (ALIAS) { if (j == 0 && more) stage_frame(frame); }
         kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
 #pragma unroll
         for (int w = 1; w < NW; w++) {
