@@ -18,6 +18,9 @@
 #include <vector>
 
 // frame groups per CTA of the 4096-point kernel (measured: 4 groups 1.58e8, 5 groups at 94 registers 1.64e8, 6 groups at 80 registers 1.61e8 spectra/s; -DSA_G12=n)
+#ifndef SA_G10
+#define SA_G10 20   // 1024-point kernel: 20 one-warp groups
+#endif
 #ifndef SA_G11
 #define SA_G11 10   // 2048-point kernel: 10 groups of 64 threads
 #endif
@@ -319,7 +322,7 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 8: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<8, 16, 16>>(ctx, p, log2n) : launch_small<SmallCfg<8>>(ctx, p);
     case 9: return (ctx->use_generic || !p.aligned8) ? launch_cfg<SpectrumCfg<9, 16, 8>>(ctx, p, log2n) : launch_small<SmallCfg<9>>(ctx, p);
     // 1024..16384 stage frames with bulk copies of the 16-byte aligned superset: any sample alignment
-    case 10: return ctx->use_generic ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, 16>>(ctx, p);
+    case 10: return ctx->use_generic ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, SA_G10>>(ctx, p);
     case 11: return ctx->use_generic ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, SA_G11>>(ctx, p);
     case 12: return ctx->use_generic ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, SA_G12>>(ctx, p);
     case 13: return ctx->use_generic ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
