@@ -24,6 +24,9 @@
 #ifndef SA_G11
 #define SA_G11 10   // 2048-point kernel: 10 groups of 64 threads
 #endif
+#ifndef SA_G13
+#define SA_G13 3    // 8192-point kernel: 3 groups of 256 threads
+#endif
 #ifndef SA_G12
 #define SA_G12 5
 #endif
@@ -325,7 +328,7 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 10: return ctx->use_generic ? launch_cfg<SpectrumCfg<10, 16, 4>>(ctx, p, log2n) : launch_v2<V2Cfg<10, SA_G10>>(ctx, p);
     case 11: return ctx->use_generic ? launch_cfg<SpectrumCfg<11, 16, 2>>(ctx, p, log2n) : launch_v2<V2Cfg<11, SA_G11>>(ctx, p);
     case 12: return ctx->use_generic ? launch_cfg<SpectrumCfg<12, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<12, SA_G12>>(ctx, p);
-    case 13: return ctx->use_generic ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, 2>>(ctx, p);
+    case 13: return ctx->use_generic ? launch_cfg<SpectrumCfg<13, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<13, SA_G13>>(ctx, p);
     case 14: return ctx->use_generic ? launch_cfg<SpectrumCfg<14, 16, 1>>(ctx, p, log2n) : launch_v2<V2Cfg<14, 1>>(ctx, p);
     case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
     default: return SA_ERR_UNSUPPORTED_LENGTH;

@@ -114,11 +114,11 @@ struct V2Cfg {
   static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
   // the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
-  // N = 2048 / 4096: the staged frame lives in the second exchange buffer (free between the last-pass reads of one frame
+  // N = 2048 / 4096 / 8192: the staged frame lives in the second exchange buffer (free between the last-pass reads of one frame
   // and the second exchange of the next), so a group needs 37 KB instead of 54 KB and five or six groups fit on
   // an SM (94 / 80 registers per thread; five measured best); the copy is issued after the statistics barrier
   // instead of after the first one
-  static constexpr bool ALIAS = (NB3 == 2 || NB3 == 4);   // N = 4096 and N = 2048 (two exchanges per frame, >= 2 warps)
+  static constexpr bool ALIAS = !FOUR && T >= 64;   // N = 2048, 4096, 8192 (two exchanges per frame, >= 2 warps per group)
   static constexpr size_t G_BUFB = ALIAS ? sizeof(float2) * M + 32 : G_BUF;   // ALIAS: unpadded exchange / frame + slack
   static constexpr size_t G_STAGE = ALIAS ? 16 : sizeof(float) * N + 32;      // samples (+16 B of alignment slack) + mbarrier
   static constexpr size_t G_BYTES = G_BUF + (NBUF - 1) * G_BUFB + G_HIST + G_MISC + G_LIST + G_STAGE;
