@@ -245,7 +245,7 @@ def run_ours(args):
     kernel_ms = ms_local / max(launches, 1)
     achieved = ALGO_BYTES_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "sa::spectrum_kernel_v2<V2Cfg<12,4>,SCALE_MUL,FULL> (one launch per step)",
+                "traffic": None, "peak_source": peak_src, "kernel": "sa::spectrum_kernel_v2<V2Cfg<12,5>,SCALE_MUL,FULL> (one launch per step)",
                 "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME, "kernel_ms": kernel_ms,
                 "fp32_tflops_algorithmic": ALGO_FLOPS_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e12}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
