@@ -68,7 +68,8 @@ typedef enum {
   SA_ERR_LIMIT_ABOVE_NYQUIST = 6,   /* InvalidFrequencyLimit(ValueAboveNyquist) */
   SA_ERR_LIMIT_INVALID_RANGE = 7,   /* InvalidFrequencyLimit(InvalidRange) */
   SA_ERR_LIMIT_TOO_NARROW = 8,      /* FrequencyLimitTooNarrow */
-  SA_ERR_SCALING = 9,               /* ScalingError: unreachable for the built-ins */
+  SA_ERR_SCALING = 9,               /* ScalingError (src/spectrum.rs:150-160): per-frame status of sa_apply_scaling_*;
+                                     * unreachable in the fused spectrum calls, whose inputs are magnitudes >= 0 */
   SA_ERR_UNSUPPORTED_LENGTH = 10,   /* reference panics (src/fft.rs:52): N > 32768 */
   SA_ERR_NON_FINITE_RESULT = 11,    /* reference panics (src/frequency.rs:52-53); per-frame status */
   /* ABI / CUDA */
@@ -96,9 +97,18 @@ typedef struct {
   uint32_t max_bin;
   float    average;
   float    median;
-  uint32_t status;    /* SA_OK, SA_ERR_NAN_VALUES, SA_ERR_INFINITY_VALUES, SA_ERR_NON_FINITE_RESULT */
-  uint32_t reserved;
+  uint32_t status;    /* SA_OK, SA_ERR_NAN_VALUES, SA_ERR_INFINITY_VALUES, SA_ERR_NON_FINITE_RESULT, SA_ERR_SCALING */
+  uint32_t reserved;  /* 0, except with SA_ERR_SCALING: row index of the offending value | SA_SCALING_ERR_* class */
 } sa_frame_stats;
+
+/* `reserved` of a frame whose status is SA_ERR_SCALING: the low 16 bits hold the row index i of the first value
+ * whose scaled image was not finite (the bin is bin_lo + i); one class bit says what the image was, so that a
+ * caller can rebuild `ScalingError(orig, new)` (src/error.rs:50-53): orig = vals[i] (left as it was), new = NaN,
+ * +Inf or -Inf. */
+#define SA_SCALING_ERR_INDEX_MASK 0x0000ffffu
+#define SA_SCALING_ERR_NAN        0x80000000u
+#define SA_SCALING_ERR_POS_INF    0x40000000u
+#define SA_SCALING_ERR_NEG_INF    0x20000000u
 
 typedef struct sa_ctx sa_ctx;
 
@@ -202,9 +212,18 @@ int sa_spectrum_single(sa_ctx *ctx, const float *h_samples, uint64_t n_samples,
                        uint32_t *n_bins, sa_frame_stats *h_stats);
 
 /* `FrequencySpectrum::apply_scaling_fn` (src/spectrum.rs:128-168) on a device-resident
- * batch: scales d_vals[f*stride + i] in place with the statistics currently in
- * d_stats[f] (and samples_len = n), then recomputes d_stats[f].  This is the repeated
- * scaling of benches/fft_spectrum_bench.rs:21-36. */
+ * batch: scales d_vals[f*stride + i] in place with the statistics of the spectrum as it is
+ * (samples_len = n; the maximum that scale_to_zero_to_one divides by is taken from the values
+ * themselves, so d_stats[f] need not hold min/max), then recomputes d_stats[f] (min/max always,
+ * average / median per stats_mask).  This is the repeated scaling of
+ * benches/fft_spectrum_bench.rs:21-36.  Error behaviour of the reference, per frame
+ * (src/spectrum.rs:150-160): values are replaced in bin order and the FIRST one whose scaled image
+ * is NaN or +-Inf stops the frame -- the values before it stay scaled, it and the rest stay as
+ * they were, the statistics are not recomputed, d_stats[f].status = SA_ERR_SCALING and
+ * d_stats[f].reserved describes the offender (SA_SCALING_ERR_*).  Reachable with the built-ins:
+ * scale_20_times_log10 of a negative (already dB) value is NaN.  Frames whose status is not SA_OK
+ * on entry hold no spectrum in the reference's terms and are left untouched.  The call itself
+ * returns SA_OK; callers check the per-frame status as after sa_spectrum_batched. */
 int sa_apply_scaling_batched(sa_ctx *ctx, float *d_vals, uint64_t n_frames, uint32_t n_bins,
                              uint64_t stride, uint32_t bin_lo, uint32_t n, int scaling_kind,
                              uint32_t stats_mask, sa_frame_stats *d_stats);

@@ -89,6 +89,9 @@ def lib(native: bool = False) -> C.CDLL:
     L.sao_spectrum_batched.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int,
                                        C.c_float, C.c_float, C.c_int, C.c_int, f32p, C.c_uint64,
                                        C.c_void_p, C.POINTER(C.c_uint32), C.c_int]
+    L.sao_apply_scaling_chain_batched.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                  C.POINTER(C.c_int), C.c_uint32, C.c_void_p,
+                                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), f32p, C.c_int]
     L.sao_sine_wave_audio_data_multiple.restype = C.c_uint64
     L.sao_sine_wave_audio_data_multiple.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                     C.POINTER(C.c_int16), C.c_uint64]
@@ -210,6 +213,26 @@ def spectrum_batched(samples, n_frames: int, n: int, frame_stride: int, sampling
                                   stats.ctypes.data_as(C.c_void_p),
                                   status.ctypes.data_as(C.POINTER(C.c_uint32)), threads)
     return code, vals[:, :n_bins], stats, status, bin_lo
+
+
+def apply_scaling_chain_batched(vals, bin0: int, n: int, kinds, stats, status, threads: int = 0):
+    """Oracle twin of `FrequencySpectrum::apply_scaling_fn(&combined(kinds))` (src/spectrum.rs:128-168) on a batch.
+    vals [frames, m] (copied), stats (STATS_DTYPE, copied), status (copied).
+    Returns (vals, stats, status, err_index, err_pair[frames, 2])."""
+    v = np.array(vals, dtype=np.float32, order="C", copy=True)
+    frames, m = v.shape
+    st = np.array(stats, dtype=STATS_DTYPE, copy=True)
+    code = np.array(status, dtype=np.uint32, copy=True)
+    err_index = np.zeros(frames, np.uint32)
+    err_pair = np.zeros((frames, 2), np.float32)
+    k = (C.c_int * len(kinds))(*kinds)
+    L = lib()
+    if threads <= 0:
+        threads = L.sao_max_threads()
+    L.sao_apply_scaling_chain_batched(_p(v), frames, m, m, bin0, n, k, len(kinds), st.ctypes.data_as(C.c_void_p),
+                                      code.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                      err_index.ctypes.data_as(C.POINTER(C.c_uint32)), _p(err_pair), threads)
+    return v, st, code, err_index, err_pair
 
 
 def sine_wave_audio_data_multiple(frequencies, sampling_rate: int, duration_ms: int) -> np.ndarray:

@@ -525,6 +525,53 @@ int sao_max_threads(void) {
 #endif
 }
 
+/* ------------------------------------------------------------------------- */
+/* FrequencySpectrum::apply_scaling_fn on a batch of spectra, src/spectrum.rs:128-168, with */
+/* scaling::combined (src/scaling.rs:174-185) as the scaling function: every function of the  */
+/* chain sees the statistics of the spectrum BEFORE the call.  Per frame: values are replaced  */
+/* in order; the first scaled value that is NaN or +-Inf returns ScalingError(orig, new)       */
+/* (:150-160) -- the values in front of it stay replaced, the rest and the statistics stay.    */
+/* Frames whose status is not OK on entry are skipped (no spectrum object exists for them).    */
+/* ------------------------------------------------------------------------- */
+int sao_apply_scaling_chain_batched(float *vals, uint64_t n_frames, uint32_t m, uint64_t stride,
+                                    uint32_t bin0, uint32_t n, const int *kinds, uint32_t n_kinds,
+                                    sao_stats *stats, uint32_t *status, uint32_t *err_index,
+                                    float *err_pair, int threads) {
+  if (threads < 1) threads = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads)
+#endif
+  {
+    vi_pair *work = (vi_pair *)malloc(sizeof(vi_pair) * 2 * (size_t)(m ? m : 1));
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int64_t f = 0; f < (int64_t)n_frames; f++) {
+      if (status[f] != SAO_OK) continue;
+      float *v = vals + (uint64_t)f * stride;
+      const sao_stats st = stats[f];                       /* :138-145, n = samples_len as f32 */
+      const float nf = (float)n;
+      int failed = 0;
+      for (uint32_t i = 0; i < m; i++) {                   /* :150 */
+        float s = v[i];
+        for (uint32_t c = 0; c < n_kinds; c++)             /* scaling.rs:176-182 */
+          s = sao_scale(kinds[c], s, st.min_val, st.max_val, st.average, st.median, nf);
+        if (isnan(s) || isinf(s)) {                        /* :155-160 */
+          status[f] = SAO_ERR_SCALING;
+          if (err_index) err_index[f] = i;
+          if (err_pair) { err_pair[2 * f] = v[i]; err_pair[2 * f + 1] = s; }
+          failed = 1;
+          break;
+        }
+        v[i] = s;                                          /* :163 */
+      }
+      if (!failed) calc_statistics_ws(v, m, bin0, &stats[f], work, work + m);   /* :166 */
+    }
+    free(work);
+  }
+  return SAO_OK;
+}
+
 int sao_spectrum_batched(const float *samples, uint64_t n_frames, uint32_t n, uint64_t frame_stride,
                          uint32_t sampling_rate, int limit_kind, float lo, float hi,
                          int window_kind, int scaling_kind, float *out_vals, uint64_t out_stride,

@@ -101,6 +101,14 @@ int sao_samples_fft_to_spectrum(const float *samples, uint64_t n, uint32_t sampl
                                 float *out_freqs, float *out_vals, uint32_t *out_n_bins,
                                 sao_stats *out_stats, float *scale_err);
 
+/* FrequencySpectrum::apply_scaling_fn (src/spectrum.rs:128-168) with scaling::combined(kinds)
+ * (src/scaling.rs:174-185) on n_frames spectra of m values each, in place; stats[f] in/out; status[f]
+ * in/out (SAO_ERR_SCALING with err_index[f] / err_pair[2f..2f+1] = (orig, new) at the first offender). */
+int sao_apply_scaling_chain_batched(float *vals, uint64_t n_frames, uint32_t m, uint64_t stride,
+                                    uint32_t bin0, uint32_t n, const int *kinds, uint32_t n_kinds,
+                                    sao_stats *stats, uint32_t *status, uint32_t *err_index,
+                                    float *err_pair, int threads);
+
 /* Batched driver = window (recomputed per frame, as the reference's callers do)
  * + sao_samples_fft_to_spectrum per frame, frames split statically over
  * `threads` OpenMP threads (the stand-in for "rayon over frames").

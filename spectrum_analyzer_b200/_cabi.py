@@ -28,6 +28,7 @@ ERR_LIMIT_ABOVE_NYQUIST = 6
 ERR_LIMIT_INVALID_RANGE = 7
 ERR_LIMIT_TOO_NARROW = 8
 ERR_SCALING = 9
+SCALING_ERR_INDEX_MASK, SCALING_ERR_NAN, SCALING_ERR_POS_INF, SCALING_ERR_NEG_INF = 0xffff, 0x80000000, 0x40000000, 0x20000000
 ERR_UNSUPPORTED_LENGTH = 10
 ERR_NON_FINITE_RESULT = 11
 ERR_INVALID_ARGUMENT = 100

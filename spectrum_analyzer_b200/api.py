@@ -319,9 +319,18 @@ class FrequencySpectrum:
         vals = np.ascontiguousarray(self._vals, dtype=np.float32).copy()
         st = np.array([self._stats], dtype=A.FRAME_STATS_DTYPE)
         karr = (C.c_int * max(len(kinds), 1))(*kinds)
+        st["status"] = A.OK          # a spectrum object exists only for frames that were OK
         _check(A.load().sa_apply_scaling_chain_host(ctx._h, vals.ctypes.data, 1, vals.size, vals.size, self._bin_lo,
                                                     self._n, karr, len(kinds), A.STATS_ALL, st.ctypes.data))
+        # the values in front of an offender are replaced, like the reference's in-place loop (src/spectrum.rs:150-163)
         self._vals = vals
+        if int(st["status"][0]) == A.ERR_SCALING:
+            r = int(st["reserved"][0])
+            i = r & A.SCALING_ERR_INDEX_MASK
+            new = float("nan") if r & A.SCALING_ERR_NAN else float("inf") if r & A.SCALING_ERR_POS_INF else float("-inf")
+            err = ScalingError(A.ERR_SCALING, f"ScalingError({float(vals[i])!r}, {new!r})")
+            err.orig, err.new = float(vals[i]), new          # ScalingError(orig, new), src/error.rs:50-53
+            raise err
         self._stats = st[0]
 
 

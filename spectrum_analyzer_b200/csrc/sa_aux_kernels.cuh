@@ -183,27 +183,67 @@ struct ScalingChain {
   int count;
 };
 
+// scaling::combined (src/scaling.rs:174-185): every step sees the same statistics.  Unlike the fused kernels
+// (whose inputs are magnitudes >= 0), a resident spectrum may already hold dB values: log10f_musl keeps libm's
+// x < 0 -> NaN and +Inf -> +Inf branches, which is what makes ScalingError reachable with the built-ins.
+__device__ __forceinline__ float apply_chain(const ScalingChain &chain, float s, float vmax) {
+  for (int c = 0; c < chain.count; c++) s = apply_scaling(chain.kind[c], s, chain.div[c], vmax);
+  return s;
+}
+
+// One CTA per frame.  Semantics of FrequencySpectrum::apply_scaling_fn (src/spectrum.rs:128-168):
+//  * the statistics handed to the scaling function are those of the spectrum BEFORE the call; the only field the
+//    built-ins read besides n is max (scale_to_zero_to_one), which is recomputed here from the values themselves
+//    (stats.max IS the maximum of the data, src/spectrum.rs:529-530), so the call does not depend on which fields
+//    the producing call was asked to fill;
+//  * values are replaced in bin order; the FIRST value whose scaled image is NaN or +-Inf stops the frame
+//    (src/spectrum.rs:150-160): the values before it stay scaled, it and everything after it stay as they were,
+//    the statistics are not recomputed, status becomes SA_ERR_SCALING and `reserved` describes the offender
+//    (row index | SA_SCALING_ERR_* class bits) so that the caller can rebuild ScalingError(orig, new);
+//  * frames whose status is not SA_OK on entry hold no spectrum in the reference's terms and are left untouched.
 __global__ void __launch_bounds__(RESCALE_THREADS) rescale_kernel(float *vals, u64 n_frames, uint32_t m, u64 stride,
                                                                    uint32_t bin_lo, const ScalingChain chain,
                                                                    uint32_t stats_mask, sa_frame_stats *stats) {
   __shared__ u64 scratch[RESCALE_THREADS / 32];
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sel[4];
+  bool needs_max = false;
+  for (int c = 0; c < chain.count; c++) needs_max |= (chain.kind[c] == SA_SCALING_ZERO_TO_ONE);
   for (u64 f = blockIdx.x; f < n_frames; f += gridDim.x) {
     float *v = vals + f * stride;
-    const float vmax = stats[f].max_val;  // statistics of the spectrum BEFORE this call (src/spectrum.rs:138-145)
-    const uint32_t status = stats[f].status;
+    if (stats[f].status != SA_OK) continue;   // block-uniform
+    __syncthreads();
+    float vmax = 0.f;
+    if (needs_max) {
+      u64 km = 0ull;
+      for (uint32_t i = threadIdx.x; i < m; i += RESCALE_THREADS) km = u64max(km, (u64)ordered_key(v[i]));
+      vmax = key_to_float((uint32_t)block_reduce_u64(km, false, scratch));
+    }
+    // pass 1: first value (in bin order) whose scaled image is not finite
+    u64 bad = ~0ull;
+    for (uint32_t i = threadIdx.x; i < m; i += RESCALE_THREADS) {
+      const float s = apply_chain(chain, v[i], vmax);
+      if (!is_finite(s)) {
+        const uint32_t cls = (s != s) ? SA_SCALING_ERR_NAN : (s > 0.f ? SA_SCALING_ERR_POS_INF : SA_SCALING_ERR_NEG_INF);
+        bad = u64min(bad, ((u64)i << 32) | cls);
+        break;   // a thread's indices ascend
+      }
+    }
+    bad = block_reduce_u64(bad, true, scratch);
+    const uint32_t stop = bad == ~0ull ? m : (uint32_t)(bad >> 32);
+    // pass 2: replace the values in front of the offender, statistics of the scaled spectrum
     u64 kmin = ~0ull, kmax = 0ull;
     float sum = 0.f;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < m; i += RESCALE_THREADS) {
-      float s = v[i];
-      for (int c = 0; c < chain.count; c++) s = apply_scaling(chain.kind[c], s, chain.div[c], vmax);  // same stats for every step
-      s = s + 0.0f;
+    for (uint32_t i = threadIdx.x; i < stop; i += RESCALE_THREADS) {
+      const float s = apply_chain(chain, v[i], vmax) + 0.0f;
       v[i] = s;
       const u64 kk = ((u64)ordered_key(s) << 32) | (bin_lo + i);
       kmin = u64min(kmin, kk); kmax = u64max(kmax, kk);
       sum += s;
+    }
+    if (stop != m) {   // block-uniform: ScalingError, statistics stay those of the spectrum before the call
+      if (threadIdx.x == 0) { stats[f].status = SA_ERR_SCALING; stats[f].reserved = stop | (uint32_t)bad; }
+      continue;
     }
     kmin = block_reduce_u64(kmin, true, scratch);
     kmax = block_reduce_u64(kmax, false, scratch);
@@ -229,12 +269,12 @@ __global__ void __launch_bounds__(RESCALE_THREADS) rescale_kernel(float *vals, u
     }
     if (threadIdx.x == 0) {
       sa_frame_stats st;
-      // min/max are always kept: the next apply_scaling_fn call reads stats.max (src/spectrum.rs:138-145)
+      // min/max are always kept (they are free here and later calls / readers may want them)
       st.min_val = key_to_float((uint32_t)(kmin >> 32)); st.min_bin = (uint32_t)kmin;
       st.max_val = key_to_float((uint32_t)(kmax >> 32)); st.max_bin = (uint32_t)kmax;
       st.average = (stats_mask & SA_STATS_AVERAGE) ? __fdiv_rn(sum, (float)m) : 0.f;
       st.median = median;
-      st.status = status;
+      st.status = SA_OK;
       st.reserved = 0;
       stats[f] = st;
     }

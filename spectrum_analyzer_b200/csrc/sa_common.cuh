@@ -75,18 +75,24 @@ __device__ __forceinline__ float db_fast(float v) {
 // ---- built-in scaling functions (src/scaling.rs:104-162), IEEE ops, no contraction ------------
 
 // musl/libm-0.2 log10f restated with explicit round-to-nearest intrinsics so that nvcc cannot
-// contract a*b+c; bit-identical to the f32 sequence of the Rust port for normal and subnormal
-// positive finite inputs (the only inputs scale_20_times_log10 passes, src/scaling.rs:108-112).
+// contract a*b+c; bit-identical to the f32 sequence of the Rust port, including libm's special cases
+// (x < 0 -> NaN, +-0 -> -Inf, +Inf / NaN -> x): a resident spectrum that already holds dB values feeds
+// negative numbers in when scale_20_times_log10 is applied again, and the NaN is what makes the reference
+// return ScalingError (src/spectrum.rs:150-160).
 __device__ __forceinline__ float log10f_musl(float x) {
   const float ivln10hi = 4.3432617188e-01f, ivln10lo = -3.1689971365e-05f,
               log10_2hi = 3.0102920532e-01f, log10_2lo = 7.9034151668e-07f,
               Lg1 = 0xaaaaaa.0p-24f, Lg2 = 0xccce13.0p-25f, Lg3 = 0x91e9ee.0p-25f, Lg4 = 0xf89e26.0p-26f;
   uint32_t ix = __float_as_uint(x);
   int k = 0;
-  if (ix < 0x00800000u) {  // subnormal: scale up
-    k -= 25;
+  if (ix < 0x00800000u || (ix >> 31)) {  // x < 2**-126
+    if ((ix << 1) == 0u) return -INFINITY;                 // log(+-0) = -inf
+    if (ix >> 31) return __uint_as_float(0x7fc00000u);      // log(-#) = NaN (also -NaN, -Inf)
+    k -= 25;                                                 // subnormal: scale up
     x = __fmul_rn(x, 33554432.0f);
     ix = __float_as_uint(x);
+  } else if (ix >= 0x7f800000u) {
+    return x;                                                // +Inf, NaN
   } else if (ix == 0x3f800000u) {
     return 0.0f;
   }

@@ -14,6 +14,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -30,11 +31,20 @@
 #ifndef SA_G12
 #define SA_G12 5
 #endif
+// frame groups per CTA of the warp-specialised 4096-point kernel (sa_spectrum_v3.cuh): G groups of 4 transform
+// warps + G statistics warps
+#ifndef SA_G12S
+#define SA_G12S 4
+#endif
+#ifndef SA_NSW12     // statistics warps per group
+#define SA_NSW12 2
+#endif
 
 #include "sa_aux_kernels.cuh"
 #include "sa_host_math.h"
 #include "sa_spectrum_kernel.cuh"
 #include "sa_spectrum_v2.cuh"
+#include "sa_spectrum_v3.cuh"
 #include "sa_spectrum_small.cuh"
 
 namespace {
@@ -73,10 +83,13 @@ struct sa_ctx {
   bool use_generic = false;   // SA_FORCE_GENERIC=1: run the generic kernel family for every N (A/B testing)
   unsigned stagger_ns = 0;    // SA_STAGGER_NS: start offset between the frame groups of a v2 CTA (tuning; measured: no effect)
   bool fast_log10 = false;    // sa_ctx_set_fast_log10
+  bool split = false;         // SA_SPLIT=1: the warp-specialised variant (sa_spectrum_v3.cuh) where one exists; measured slower
+                              // than the one-role kernel at cfg2 (1.65e8 vs 1.70e8 spectra/s, profiles/README.md), so opt-in
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
   KernelPlan plans[16];                                     // per log2n (generic family)
   KernelPlan plans_v2[16][4][2];                            // tuned family: [log2n][scale mode][full range]
+  KernelPlan plans_v3[16][4][2];                            // warp-specialised variant of the tuned family
   std::map<uint32_t, float2 *> v2_tables;                   // n -> tw2 | tw3 | twr (one allocation)
   KernelPlan plans_small[16][4][2];                         // small-N family
   std::map<uint32_t, float2 *> small_tables;                // n -> tw2 | twr
@@ -199,6 +212,31 @@ int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
   return SA_OK;
 }
 
+// warp-specialised variant: same tables, NT + 32 G threads
+template <class C, int MODE, bool FULL>
+int launch_v3_inst(sa_ctx *ctx, const V2Params &P) {
+  KernelPlan &plan = ctx->plans_v3[C::LOG2N][MODE][FULL ? 1 : 0];
+  auto kernel = spectrum_kernel_v3<C, MODE, FULL>;
+  if (!plan.ready) {
+    SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TOTAL));
+    int per_sm = 0;
+    SA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, C::NT_ALL, C::SMEM_TOTAL));
+    if (per_sm < 1) { g_last_error = "v3 kernel does not fit on an SM"; return SA_ERR_CUDA; }
+    plan.max_blocks = per_sm * ctx->num_sms;
+    plan.ready = true;
+  }
+  const u64 needed = (P.b.n_frames + C::G - 1) / C::G;
+  const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
+  kernel<<<grid, C::NT_ALL, C::SMEM_TOTAL, ctx->stream>>>(P);
+  ctx->launches++;
+  SA_CUDA(cudaGetLastError());
+  return SA_OK;
+}
+
+// the warp-specialised configuration of a size (void: none)
+template <int LOG2N> struct SplitCfg { using type = void; };
+template <> struct SplitCfg<12> { using type = V2Cfg<12, SA_G12S, SA_NSW12>; };
+
 template <class C>
 int launch_v2(sa_ctx *ctx, const SpectrumParams &p) {
   V2Params P;
@@ -220,6 +258,18 @@ int launch_v2(sa_ctx *ctx, const SpectrumParams &p) {
       break;
     case SA_SCALING_ZERO_TO_ONE: mode = SCALE_ZERO_ONE; break;
     default: mode = SCALE_LOG10; break;
+  }
+  using CS = typename SplitCfg<C::LOG2N>::type;
+  if constexpr (!std::is_void<CS>::value) {
+    // statistics wanted: the warp-specialised kernel (the statistics warp is what writes records and rows)
+    if (p.stats != nullptr && ctx->split) {
+      switch (mode) {
+        case SCALE_MUL: return full ? launch_v3_inst<CS, SCALE_MUL, true>(ctx, P) : launch_v3_inst<CS, SCALE_MUL, false>(ctx, P);
+        case SCALE_DIV: return full ? launch_v3_inst<CS, SCALE_DIV, true>(ctx, P) : launch_v3_inst<CS, SCALE_DIV, false>(ctx, P);
+        case SCALE_ZERO_ONE: return full ? launch_v3_inst<CS, SCALE_ZERO_ONE, true>(ctx, P) : launch_v3_inst<CS, SCALE_ZERO_ONE, false>(ctx, P);
+        default: return full ? launch_v3_inst<CS, SCALE_LOG10, true>(ctx, P) : launch_v3_inst<CS, SCALE_LOG10, false>(ctx, P);
+      }
+    }
   }
 #define SA_V2_CASE(M_) \
   case M_: return full ? launch_v2_inst<C, M_, true>(ctx, P) : launch_v2_inst<C, M_, false>(ctx, P);
@@ -312,6 +362,10 @@ int launch_small(sa_ctx *ctx, const SpectrumParams &p) {
 
 int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
   if (p.n_frames == 0) return SA_OK;
+#ifdef SA_ONLY_4096   // experiment builds (profiles/microbench): compile the headline size only
+  if (log2n != 12) return SA_ERR_UNSUPPORTED_LENGTH;
+  return launch_v2<V2Cfg<12, SA_G12>>(ctx, p);
+#else
   switch (log2n) {
     case 1: case 2: case 3: case 4: case 5: {
       const unsigned grid = (unsigned)((p.n_frames + 127) / 128);
@@ -333,6 +387,7 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
     case 15: return launch_cfg<SpectrumCfg<15, 16, 1>>(ctx, p, log2n);
     default: return SA_ERR_UNSUPPORTED_LENGTH;
   }
+#endif
 }
 
 // Call-level validation in the reference's order (src/lib.rs:164-181, src/fft.rs:52, src/lib.rs:317).
@@ -481,6 +536,8 @@ int sa_ctx_create_on_stream(int device, void *cuda_stream, sa_ctx **out_ctx) {
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   const char *fg = getenv("SA_FORCE_GENERIC");
   ctx->use_generic = fg && fg[0] == '1';
+  const char *ns = getenv("SA_SPLIT");
+  ctx->split = ns && ns[0] == '1';
   if (const char *st = getenv("SA_STAGGER_NS")) ctx->stagger_ns = (unsigned)strtoul(st, nullptr, 10);
   *out_ctx = ctx;
   return SA_OK;

@@ -67,9 +67,19 @@ struct V2Params {
   unsigned stagger_ns; // start offset between the frame groups of a CTA (see the kernel)
 };
 
-template <int LOG2N_, int G_>
+template <int LOG2N_, int G_, int NSW_ = 0>
 struct V2Cfg {
+  static constexpr bool SPLIT_ = NSW_ > 0;
   static constexpr int LOG2N = LOG2N_, N = 1 << LOG2N_, M = N / 2, E = 16, T = M / E, G = G_, NT = T * G_;
+  // SPLIT: warp-specialised variant (sa_spectrum_v3.cuh).  The T threads of a group only transform, scale and
+  // histogram a frame; one extra "statistics warp" per group (threads NT .. NT + 32 G) finishes the frame from a
+  // copy of the scaled values in shared memory while the group already transforms its next frame.
+  // NSW statistics warps per group: with two, consecutive frames of a group go to alternate warps, each with its own
+  // copy of the values, histogram and partial-result slots, so that a statistics warp has two frame times per frame.
+  static constexpr bool SPLIT = SPLIT_;
+  static constexpr int NSW = NSW_;
+  static_assert(NSW_ == 0 || NSW_ == 1 || NSW_ == 2, "statistics warps per group");
+  static constexpr int NT_ALL = NT + 32 * G_ * NSW_;
   static constexpr int NW = T / 32;                  // warps per group
   static constexpr bool FOUR = (M > 4096);           // N = 16384: passes 16,16,16,R4 instead of 16,16,R3
   static constexpr int R3 = FOUR ? 16 : M / 256;     // radix of the third pass (last pass unless FOUR)
@@ -82,7 +92,12 @@ struct V2Cfg {
 #ifndef SA_HBITS
 #define SA_HBITS 6
 #endif
-  static constexpr int HBITS = SA_HBITS, NBUCKET = 1 << HBITS;
+  // the warp-specialised variant scans the histogram once per frame (not once per warp) and ranks the selected
+  // bucket in its one statistics warp: more, finer buckets pay there (fewer candidates to gather and rank)
+#ifndef SA_HBITS_SPLIT
+#define SA_HBITS_SPLIT 8
+#endif
+  static constexpr int HBITS = SPLIT_ ? SA_HBITS_SPLIT : SA_HBITS, NBUCKET = 1 << HBITS;
   static constexpr int HBPL = NBUCKET / 32;               // buckets per lane of the scanning warp
   // the per-thread constants (window multipliers, pass twiddles, recombination
   // twiddles: 112 words per thread) in tensor memory, read with tcgen05.ld (sa_tmem.cuh): column
@@ -109,9 +124,9 @@ struct V2Cfg {
   // with __syncwarp, which is cheap enough to reuse a single buffer and leave room for the staging buffer
   static constexpr int NBUF = T == 32 ? 1 : 2;
   static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
-  static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * 2;      // two histograms, alternated per frame
+  static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * (SPLIT_ ? NSW_ : 2);   // two histograms, alternated per frame (SPLIT: one per statistics warp)
   static constexpr size_t G_MISC = sizeof(uint32_t) * 96;
-  static constexpr size_t G_LIST = sizeof(uint32_t) * 32;
+  static constexpr size_t G_LIST = sizeof(uint32_t) * 32 * (NSW_ > 1 ? NSW_ : 1);
   // the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
   // N = 2048 / 4096 / 8192: the staged frame lives in the second exchange buffer (free between the last-pass reads of one frame
@@ -121,14 +136,26 @@ struct V2Cfg {
   static constexpr bool ALIAS = !FOUR && T >= 64;   // N = 2048, 4096, 8192 (two exchanges per frame, >= 2 warps per group)
   static constexpr size_t G_BUFB = ALIAS ? sizeof(float2) * M + 32 : G_BUF;   // ALIAS: unpadded exchange / frame + slack
   static constexpr size_t G_STAGE = ALIAS ? 16 : sizeof(float) * N + 32;      // samples (+16 B of alignment slack) + mbarrier
-  static constexpr size_t G_BYTES = G_BUF + (NBUF - 1) * G_BUFB + G_HIST + G_MISC + G_LIST + G_STAGE;
+  // SPLIT: three more mbarriers (full / empty / second buffer free) and the scaled values of one frame, bin b at
+  // float index b + o with o = (output row address / 4) mod 4, so that 16-byte chunks of the copy and of the
+  // output row coincide (vector stores although rows of M + 1 floats are only 4-byte aligned)
+  static constexpr size_t G_SYNC = SPLIT_ ? 48 : 0;      // full[2], empty[2], second buffer free
+  static constexpr int VALS_FLOATS = M + 4;
+  static constexpr size_t G_VALS = sizeof(float) * VALS_FLOATS * NSW_;
+  static constexpr size_t G_BYTES = G_BUF + (NBUF - 1) * G_BUFB + G_HIST + G_MISC + G_LIST + G_STAGE + G_SYNC + G_VALS;
+  static_assert(G_BYTES % 16 == 0, "group blocks stay 16-byte aligned");
   static constexpr size_t SMEM_TOTAL = OFF_GROUPS + G_BYTES * G_;
 };
 
 // misc words of a group
 enum { MI_KMIN = 0, MI_KMAX = 16, MI_SUM = 32, MI_ARGMIN = 48, MI_ARGMAX = 49, MI_LCOUNT = 50,
        MI_GUESS = 51, MI_SELA = 52 /*b, below, cnt*/, MI_LDONE = 55, MI_SELB = 56, MI_RESA = 57, MI_RESB = 58,
-       MI_FLAGS = 59, MI_UMAX = 64 };
+       MI_FLAGS = 59, MI_WINL = 60 /* SPLIT: two windows published by the statistics warp: {klo, shift | use << 8} per frame parity */,
+       MI_UMAX = 64, MI_BMIN = 80, MI_BMAX = 88 /* SPLIT: per warp, the lanes that hold the warp's minimum / maximum */ };
+// misc words of a group in the split variant (the words above except MI_UMAX are unused there).  [s]: hand-over slot
+// (statistics warp) s = frame parity when NSW = 2, 0 when NSW = 1; [p]: frame parity.
+enum { MS_KMIN = 0 /* [s][8] */, MS_KMAX = 16 /* [s][8] */, MS_SUM = 32 /* [s][8] */, MS_BMIN = 48 /* [s][4] */, MS_BMAX = 56 /* [s][4] */,
+       MS_WIN = 80 /* [p] {klo, shift | use << 8} */, MS_FLAGS = 84 /* [s] */, MS_LCOUNT = 86 /* [s] */ };
 
 // Histogram slot of key k for the candidate window [klo, klo + width] with bucket shift sh:
 // slot 0 = below the window, slots 1..NB = buckets, slot NB+1 = above.  The atomic increment is
@@ -195,6 +222,32 @@ __device__ __forceinline__ bool frame_max_is_fast_divisor(float d) {
   return b >= 0x00800000u && b < 0x7f800000u && (b & 0x007fffffu) != 0x007fffffu;   // normal, finite, not all ones
 }
 
+// Bin index of val[i] of (logical) thread j -- the same dealing of the last-pass butterflies as in the body below
+// (MIRROR for N = 4096, the generic mirrored list for N = 1024 / 2048 / 16384, shuffle-mirrored lanes for N = 8192),
+// as a function of run-time (j, i): used by the statistics warp of the split variant to find a thread's bins.
+template <class C>
+__device__ __forceinline__ uint32_t v2_binof(int j, int i) {
+  constexpr int M = C::M, T = C::T;
+  constexpr int LR = C::FOUR ? C::R4 : C::R3, LNB = C::FOUR ? C::NB4 : C::NB3, LS = LNB * T;
+  constexpr bool MIRROR = (C::NB3 == 2), MIRG = !MIRROR && LNB >= 2;
+  uint32_t k;
+  if constexpr (MIRROR) {
+    const int jbB = j ? 256 - j : 128;
+    const int q = i >> 2, r = i & 3;
+    k = (uint32_t)(((r & 2) ? jbB : j) + 256 * q);
+    return (r & 1) ? (uint32_t)M - k : k;
+  } else if constexpr (MIRG) {
+    const int pidx = i >> 1, sl = pidx / LR, rem = pidx % LR;
+    const int a = j + sl * T, b = j ? LS - (j + sl * T) : (sl ? LS - sl * T : LS / 2);
+    k = (uint32_t)(((rem & 1) ? b : a) + (rem >> 1) * LS);
+    return (i & 1) ? (uint32_t)M - k : k;
+  } else {
+    const int beta = (j & 31) < 16 ? 16 * (j >> 5) + (j & 31) : (j == 16 ? 128 : 256 - (16 * (j >> 5) + (j & 31) - 16));
+    k = (uint32_t)(beta + (i >> 1) * 256);
+    return (i & 1) ? (uint32_t)M - k : k;
+  }
+}
+
 template <class C, int MODE, bool FULL>
 __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned char *smem, const uint32_t tm_base) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, G = C::G, NW = C::NW, R3 = C::R3, NB3 = C::NB3;
@@ -232,6 +285,14 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   unsigned char *stage = ALIAS ? reinterpret_cast<unsigned char *>(bufB) : tail;
   uint64_t *mbar = reinterpret_cast<uint64_t *>(ALIAS ? tail : tail + sizeof(float) * N + 16);
   uint32_t phase = 0;              // parity of the mbarrier phase the next wait completes
+  // SPLIT: hand-over to the group's statistics warp
+  unsigned char *sync_base = gbase + OFF_HIST + C::G_HIST + C::G_MISC + C::G_LIST + C::G_STAGE;
+  uint64_t *mb_full = reinterpret_cast<uint64_t *>(sync_base);        // [slot] NW arrivals: values + partials of a frame are in place
+  uint64_t *mb_empty = reinterpret_cast<uint64_t *>(sync_base + 16);  // [slot] 1 arrival: the statistics warp is done with them
+  uint32_t *bfree_cnt = reinterpret_cast<uint32_t *>(sync_base + 32);  // warps that have read their last-pass inputs: the last one stages the next frame
+  float *vbuf0 = reinterpret_cast<float *>(sync_base + C::G_SYNC);    // [slot] copies of the scaled values
+  uint32_t ephase = 0;               // bit s = parity of the next wait on empty[s]
+  uint32_t fcount = 0;               // frames handed over so far
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
 #ifndef SA_GW_MIN_LOG2
 #define SA_GW_MIN_LOG2 17
@@ -322,9 +383,16 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   }
   // window multiplier from global memory (rare paths only)
   auto win1 = [&](int n) -> float { return has_win ? __ldg(p.window + n) : 1.0f; };
-  for (int i = j; i < 2 * C::HSTRIDE; i += T) hist0[i] = 0;
+  for (int i = j; i < (int)(C::G_HIST / sizeof(uint32_t)); i += T) hist0[i] = 0;
   if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
-  if (j == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
+  if (j == 0) {
+    mbar_init(mbar, 1);
+    if constexpr (C::SPLIT) {
+      for (int q = 0; q < C::NSW; q++) { mbar_init(mb_full + q, NW); mbar_init(mb_empty + q, 1); }
+      *bfree_cnt = 0u;
+    }
+    mbar_fence_init();
+  }
   __syncthreads();
   tmem_fence_after_sync();
 
@@ -337,6 +405,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   u64 frame = (u64)blockIdx.x * G + g;
   const u64 fstep = (u64)gridDim.x * G;
   if (frame >= p.n_frames) return;  // group-uniform; no CTA-wide barrier after this point
+  // SPLIT: position of bin 0 of a frame inside its copy, (output row address / 4) mod 4 (see V2Cfg::G_VALS)
+  uint32_t o_pos = (uint32_t)(((reinterpret_cast<uintptr_t>(p.out_vals) >> 2) + frame * p.out_stride - p.bin_lo) & 3u);
+  const uint32_t o_step = (uint32_t)((fstep * p.out_stride) & 3u);
   // Tuning hook (SA_STAGGER_NS, default 0): start the groups a fraction of a frame time apart.  Measured: no
   // effect -- the groups drift apart by themselves.
   if (G > 1 && g > 0 && P.stagger_ns) __nanosleep((unsigned)g * P.stagger_ns);
@@ -352,6 +423,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // thread 0 of the group: bulk copy of frame f into the staging buffer
   const bool al16 = p.aligned16 != 0;   // launch-uniform: every frame starts on a 16-byte boundary
   auto stage_frame = [&](u64 f) {
+    // the target was last read / written through the generic proxy (exchange data, sample loads): order those
+    // accesses (made visible to this thread by the preceding barrier) before the async-proxy write of the copy
+    fence_proxy_async();
     const uintptr_t a = frame_addr(f);
     if (al16) {
       mbar_arrive_expect_tx(mbar, (uint32_t)N * esz);
@@ -444,7 +518,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     group_sync<T>(g);
     // every thread of the group has consumed the staged samples and finished the previous frame
     if constexpr (!ALIAS) { if (j == 0 && more) stage_frame(frame + fstep); }
-    if (want_stats && rec_thread) flush_record();
+    if constexpr (!C::SPLIT) { if (want_stats && rec_thread) flush_record(); }
     {
       const float2 *r = wbuf + (j + (j >> 4));
 #pragma unroll
@@ -474,6 +548,17 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
       for (int k = 0; k < 8; k++) { x[k] = wbuf[j + 256 * k]; x[8 + k] = wbuf[jbB + 256 * k]; }
       { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
+      if constexpr (C::SPLIT && ALIAS) {
+        // every warp has read its last-pass inputs -> the next frame may land in buffer B: the LAST warp to get
+        // here issues the bulk copy (as early as possible: the data is needed at the top of the next iteration)
+        __syncwarp();
+        if (lane == 0) {
+          if (atoms_add_acq_rel(bfree_cnt, 1u) == (uint32_t)(NW - 1)) {
+            *bfree_cnt = 0u;           // next used after two group barriers
+            if (more) stage_frame(frame + fstep);
+          }
+        }
+      }
       {
         float2 va[8], vb[8];
         va[0] = x[0]; vb[0] = x[8];
@@ -534,6 +619,17 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         for (int s = 0; s < 16; s++) x[s] = r[s * T];
       }
       { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
+      if constexpr (C::SPLIT && ALIAS) {
+        // every warp has read its last-pass inputs -> the next frame may land in buffer B: the LAST warp to get
+        // here issues the bulk copy (as early as possible: the data is needed at the top of the next iteration)
+        __syncwarp();
+        if (lane == 0) {
+          if (atoms_add_acq_rel(bfree_cnt, 1u) == (uint32_t)(NW - 1)) {
+            *bfree_cnt = 0u;           // next used after two group barriers
+            if (more) stage_frame(frame + fstep);
+          }
+        }
+      }
 
       if constexpr (C::FOUR) {
         // ---- pass 3: radix 16, NS = 256 (one butterfly per thread) ---------------------------------
@@ -748,6 +844,110 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
     if constexpr (MODE == SCALE_MUL) vmid = scale1(vmid);
 
+    if constexpr (C::SPLIT) {
+      // ---- hand-over to the group's statistics warp (sa_spectrum_v3.cuh) -----------------------------
+      // per-thread min / max / sum and the non-finite check stay here (the values are in registers); everything
+      // that needs the whole frame -- arg bins, median, average, record, the stores -- happens in the other warp
+      uint32_t kmn = 0xffffffffu, kmx = 0u;
+      float sum = 0.f;
+      if constexpr (FULL) {
+        float2 acc = make_float2(val[0], val[1]);
+#pragma unroll
+        for (int i = 2; i < E; i += 2) acc = add2(acc, make_float2(val[i], val[i + 1]));
+        sum = acc.x + acc.y;
+#pragma unroll
+        for (int i = 0; i < E; i += 2) {
+          const uint32_t k0 = v2_key<MODE>(val[i]), k1 = v2_key<MODE>(val[i + 1]);
+          kmn = min(kmn, min(k0, k1));
+          kmx = max(kmx, max(k0, k1));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < E; i++) {   // dropped bins become +Inf: above every finite key, never a candidate
+          const bool keep = SA_VALID(i);
+          if (keep) {
+            const uint32_t k = v2_key<MODE>(val[i]);
+            kmn = min(kmn, k);
+            kmx = max(kmx, k);
+            sum += val[i];
+          }
+          val[i] = keep ? val[i] : __uint_as_float(0x7f800000u);
+        }
+      }
+      if (valid_mid) {
+        const uint32_t k = v2_key<MODE>(vmid);
+        kmn = min(kmn, k);
+        kmx = max(kmx, k);
+        sum += vmid;
+      }
+      const uint32_t my_kmn = kmn, my_kmx = kmx;
+      kmn = __reduce_min_sync(0xffffffffu, kmn);
+      kmx = __reduce_max_sync(0xffffffffu, kmx);
+      // which lanes hold the warp's extremes: the statistics warp only looks at their bins for the arg bins
+      const uint32_t bmn = __ballot_sync(0xffffffffu, my_kmn == kmn), bmx = __ballot_sync(0xffffffffu, my_kmx == kmx);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      // non-finite spectrum value (warp-uniform; a NaN / Inf sample makes every bin non-finite, so every warp of
+      // the group sees it): classify NaN / Inf in the windowed input, each warp over all N samples
+      bool nonfinite;
+      if constexpr (MODE == SCALE_LOG10 || MODE == SCALE_ZERO_ONE) nonfinite = (__float_as_uint(umax) >= 0x7f800000u);
+      else nonfinite = (kmx >= 0x7f800000u);
+      uint32_t fl = 0u;
+      if (nonfinite) {
+        fl = 4u;
+        for (int n = lane; n < N; n += 32) {
+          const float v = __fmul_rn(win1(n), load_sample(p, cur * p.frame_stride + n));
+          if (v != v) fl |= 1u;
+          if (fabsf(v) == INFINITY) fl |= 2u;
+        }
+        fl = __reduce_or_sync(0xffffffffu, fl);
+      }
+      // the statistics warp is done with the previous frame: its window for this frame is published
+      const int slot = C::NSW > 1 ? par : 0;          // hand-over slot = statistics warp of this frame
+      if (fcount >= (uint32_t)C::NSW) { mbar_wait_sleep(mb_empty + slot, (ephase >> slot) & 1u); ephase ^= 1u << slot; }
+      fcount++;
+      float *vbuf = vbuf0 + slot * C::VALS_FLOATS;
+      {
+        // window of this frame's parity: published by the statistics warp two frames ago
+        const uint2 wp = *reinterpret_cast<const uint2 *>(&misc[MS_WIN + 2 * par]);   // {klo, shift | use << 8}
+        if ((wp.y & 0x100u) && !(SA_EXP & 0x8000)) {
+          uint32_t *hist = hist0 + slot * C::HSTRIDE + 3;   // hist[0] = below, hist[1 + b] = bucket b, hist[NBUCKET + 1] = above (clean: see the statistics warp)
+          const int shw = (int)(wp.y & 0xffu);
+#pragma unroll
+          for (int i = 0; i < E; i++)   // unconditional: dropped bins are +Inf and count as "above"
+            atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(val[i]), wp.x, shw)], 1u);
+          if (valid_mid) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(vmid), wp.x, shw)], 1u);
+        }
+      }
+      {
+        // bin b of the frame at float index b + o of the copy (o: see V2Cfg::G_VALS)
+        const uint32_t o = o_pos;
+        o_pos = (o_pos + o_step) & 3u;
+        float *vb = vbuf + o;
+        if constexpr (MIRROR) {
+          float *d0 = vb + j, *d1 = vb + (M - j), *d2 = vb + jbB, *d3 = vb + (M - jbB);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            d0[256 * q] = val[4 * q];
+            d1[-256 * q] = val[4 * q + 1];
+            d2[256 * q] = val[4 * q + 2];
+            d3[-256 * q] = val[4 * q + 3];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < E; i++) vb[binof(i)] = val[i];
+        }
+        if (j == 0) vb[M / 2] = valid_mid ? vmid : __uint_as_float(0x7f800000u);
+      }
+      if (lane == 0) {
+        misc[MS_KMIN + 8 * slot + wig] = kmn; misc[MS_KMAX + 8 * slot + wig] = kmx; misc[MS_SUM + 8 * slot + wig] = __float_as_uint(sum);
+        misc[MS_BMIN + 4 * slot + wig] = bmn; misc[MS_BMAX + 4 * slot + wig] = bmx;
+        if (fl) atomicOr(&misc[MS_FLAGS + slot], fl);
+      }
+      par ^= 1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mb_full + slot);
+    } else {
     if constexpr (ALIAS) {
       if (!want_stats) {   // no statistics barrier to hang the copy on: one extra group barrier
         group_sync<T>(g);
@@ -1239,11 +1439,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
       if (valid_mid) dst[M / 2] = vmid;
     }
+    }   // !SPLIT
 
 #undef SA_VALID
     if (!more) break;
   }
-  if (want_stats) {
+  if (want_stats && !C::SPLIT) {
     group_sync<T>(g);                 // every thread of the group has finished its last frame
     if (rec_thread) flush_record();
   }

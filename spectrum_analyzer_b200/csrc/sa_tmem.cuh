@@ -81,11 +81,39 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// one arrival (release at CTA scope: the arriving thread's earlier shared-memory accesses, and those of the
+// threads it synchronised with before, happen before whatever a waiter does after its wait)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory counter with acquire-release semantics at CTA scope: the thread that sees the last count may act on
+// what the earlier arrivals (and the threads they synchronised with) did before arriving
+__device__ __forceinline__ uint32_t atoms_add_acq_rel(uint32_t *addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;\n" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
+}
+// Orders earlier generic-proxy accesses to shared memory before later async-proxy accesses (bulk copies) to it.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// The same for waits that are expected to take a while (role hand-over): the hint lets the hardware keep the warp
+// suspended instead of re-issuing the probe, which would compete with the warp that is being waited for.
+#ifndef SA_MBAR_HINT_NS
+#define SA_MBAR_HINT_NS 2000
+#endif
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+  if (SA_MBAR_HINT_NS == 0) { mbar_wait(bar, parity); return; }
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.b32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SA_MBAR_HINT_NS) : "memory");
   } while (!done);
 }
 
