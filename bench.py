@@ -245,7 +245,7 @@ def run_ours(args):
     kernel_ms = ms_local / max(launches, 1)
     achieved = ALGO_BYTES_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "sa::spectrum_kernel_v2<V2Cfg<12,5>,SCALE_MUL,FULL> (one launch per step)",
+                "traffic": None, "peak_source": peak_src, "kernel": ctx.last_kernel + " (one launch per step)",
                 "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME, "kernel_ms": kernel_ms,
                 "fp32_tflops_algorithmic": ALGO_FLOPS_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e12}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
@@ -295,11 +295,40 @@ def run_ours(args):
                    "h2d_bytes_per_step": ef * N * 4, "d2h_bytes_per_step": ef * (out_stride * 4 + 32),
                    "frames_per_step": ef, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                    "api": "sa_spectrum_batched_host (pinned host buffers, 3-slot H2D/compute/D2H pipeline)"}
+            # copy-only ceiling of this box at this N: the same bytes over the same pinned buffers, H2D and D2H
+            # concurrently on two streams, no kernel -- what a perfect pipeline could reach (all ranks at once)
+            try:
+                s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+                dvals = vals[: ef * out_stride]
+                dst = torch.empty(ef * N, dtype=torch.float32, device=dev)
+
+                def copy_step():
+                    with torch.cuda.stream(s_in):
+                        dst.copy_(hx, non_blocking=True)
+                    with torch.cuda.stream(s_out):
+                        hv.copy_(dvals, non_blocking=True)
+                        hs.copy_(stats[: ef * 32], non_blocking=True)
+                copy_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    copy_step()
+                torch.cuda.synchronize(dev)
+                dtc = max_over_ranks(time.perf_counter() - t0)
+                barrier()
+                ceil = world * ef * args.e2e_steps / dtc
+                e2e["copy_ceiling"] = {"value": ceil, "unit": UNIT,
+                                       "h2d_gbs_per_gpu": ef * N * 4 * args.e2e_steps / dtc / 1e9,
+                                       "d2h_gbs_per_gpu": ef * (out_stride * 4 + 32) * args.e2e_steps / dtc / 1e9,
+                                       "how": "cudaMemcpyAsync of the step's input (H2D) and output (D2H) on two streams, "
+                                              "concurrently on all ranks, no kernel"}
+                e2e["frac_of_copy_ceiling"] = e2e["value"] / ceil
+                del dst
+            except RuntimeError as ex:
+                e2e["copy_ceiling"] = {"error": str(ex)[:200]}
             # beside it (not the headline): the same frames as int16 PCM through sa_spectrum_batched_host_i16 --
             # the host->device copy, the limiter of the f32 call, is halved
             try:
-                if world > 1:
-                    raise RuntimeError("single-GPU side measurement only")
                 hx16 = torch.empty(ef * N, dtype=torch.int16, pin_memory=True)
                 hx16.copy_((hx * 8192.0).clamp_(-32768, 32767).to(torch.int16))
 
@@ -321,6 +350,33 @@ def run_ours(args):
                 del hx16
             except RuntimeError:
                 pass
+            # the same call from PAGEABLE host memory (what a caller holding a plain Vec<f32> / numpy array pays):
+            # a quarter of the frames, one step after one warm-up
+            try:
+                import numpy as np
+                pf = max(1024, ef // 4)
+                px = np.empty(pf * N, dtype=np.float32)
+                px[:] = hx[: pf * N].numpy()
+                pv = np.empty(pf * out_stride, dtype=np.float32)
+                ps = np.empty(pf * 32, dtype=np.uint8)
+
+                def e2e_step_pageable():
+                    chk(lib.sa_spectrum_batched_host(ectx._h, px.ctypes.data, pf, N, N, SAMPLING_RATE, cabi.LIMIT_ALL, 0.0,
+                                                     0.0, cabi.WINDOW_HANN, cabi.SCALING_DIVIDE_BY_N_SQRT, stats_mask,
+                                                     pv.ctypes.data, out_stride, ps.ctypes.data, None, None))
+                e2e_step_pageable()
+                barrier()
+                t0 = time.perf_counter()
+                e2e_step_pageable()
+                dtp = max_over_ranks(time.perf_counter() - t0)
+                barrier()
+                assert np.array_equal(pv[: 64 * out_stride], vals[: 64 * out_stride].cpu().numpy()), "pageable e2e output != device output"
+                e2e["pageable_input"] = {"value": world * pf / dtp, "unit": UNIT, "frames_per_step": pf,
+                                         "h2d_bytes_per_step": pf * N * 4, "d2h_bytes_per_step": pf * (out_stride * 4 + 32),
+                                         "api": "sa_spectrum_batched_host from pageable numpy arrays"}
+                del px, pv, ps
+            except (RuntimeError, MemoryError) as ex:
+                e2e["pageable_input"] = {"error": str(ex)[:200]}
             del hx, hv, hs
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------------

@@ -132,6 +132,9 @@ int sa_ctx_sync(sa_ctx *ctx);
 int sa_ctx_set_fast_log10(sa_ctx *ctx, int enable);
 /* Number of kernels this context has launched so far (for bench accounting). */
 uint64_t sa_ctx_launch_count(const sa_ctx *ctx);
+/* Name of the spectrum kernel the last sa_spectrum_* call on this context launched (template arguments included),
+ * e.g. "sa::spectrum_kernel_v2<V2Cfg<12,5,0>,0,1>": what profiles and bench lines cite.  No reference counterpart. */
+const char *sa_ctx_last_kernel(const sa_ctx *ctx);
 
 /* ---- host-side pieces of the path (no GPU needed) ------------------------- */
 
@@ -167,10 +170,11 @@ int sa_bin_frequencies(uint32_t n, uint32_t sampling_rate, uint32_t bin_lo, uint
  *               then per-frame validation results are not reported)
  * Host outputs: *bin_lo, *n_bins (may be NULL).
  * n must be a power of two in [2, 32768]; out_stride >= n_bins.
- * Alignment: none beyond the element type's.  Frames of n >= 1024 samples are staged by bulk
- * copies of their 16-byte aligned superset, which may read up to 15 bytes before the first and
- * after the last sample of the batch (inside the allocation granule of any CUDA allocation, never
- * written, never used); 16-byte aligned frames (base pointer and hop) take the fastest path.
+ * Alignment: the element type's for d_samples (checked: SA_ERR_INVALID_ARGUMENT otherwise), 4 bytes for
+ * d_out_vals, 16 bytes for d_stats.  No byte outside [d_samples, d_samples + (n_frames-1)*frame_stride + n)
+ * is read: frames of n >= 1024 samples that do not start on a 16-byte boundary are staged by bulk copies of
+ * their 16-byte aligned superset, clamped at the two ends of the batch (the few bytes there are fetched by
+ * ordinary loads).  16-byte aligned frames (base pointer and hop) take the fastest path.
  */
 int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, uint32_t n,
                         uint64_t frame_stride, uint32_t sampling_rate, int limit_kind,

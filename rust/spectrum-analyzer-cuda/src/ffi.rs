@@ -34,6 +34,7 @@ extern "C" {
     pub fn sa_ctx_sync(ctx: *mut sa_ctx) -> c_int;
     pub fn sa_ctx_set_fast_log10(ctx: *mut sa_ctx, enable: c_int) -> c_int;
     pub fn sa_ctx_launch_count(ctx: *const sa_ctx) -> u64;
+    pub fn sa_ctx_last_kernel(ctx: *const sa_ctx) -> *const c_char;
     pub fn sa_window_coeffs(window_kind: c_int, n: u32, host_out: *mut f32) -> c_int;
     pub fn sa_limit_to_bins(n: u32, sampling_rate: u32, limit_kind: c_int, limit_lo: f32, limit_hi: f32,
                             bin_lo: *mut u32, n_bins: *mut u32) -> c_int;

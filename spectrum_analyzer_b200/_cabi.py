@@ -59,6 +59,7 @@ SYMBOLS = {
     "sa_ctx_sync": (_i, [_vp]),
     "sa_ctx_set_fast_log10": (_i, [_vp, _i]),
     "sa_ctx_launch_count": (_u64, [_vp]),
+    "sa_ctx_last_kernel": (C.c_char_p, [_vp]),
     "sa_window_coeffs": (_i, [_i, _u32, _vp]),
     "sa_limit_to_bins": (_i, [_u32, _u32, _i, _f, _f, _u32p, _u32p]),
     "sa_bin_frequencies": (_i, [_u32, _u32, _u32, _u32, _vp]),

@@ -195,6 +195,11 @@ class Context:
     def launch_count(self) -> int:
         return int(A.load().sa_ctx_launch_count(self._h))
 
+    @property
+    def last_kernel(self) -> str:
+        """Name (with template arguments) of the spectrum kernel the last call on this context launched."""
+        return (A.load().sa_ctx_last_kernel(self._h) or b"").decode()
+
 
 _default_ctx: dict[int, Context] = {}
 

@@ -14,6 +14,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -80,6 +81,7 @@ struct sa_ctx {
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   uint64_t launches = 0;
+  char last_kernel[96] = "";  // name of the last spectrum kernel launched (sa_ctx_last_kernel)
   bool use_generic = false;   // SA_FORCE_GENERIC=1: run the generic kernel family for every N (A/B testing)
   unsigned stagger_ns = 0;    // SA_STAGGER_NS: start offset between the frame groups of a v2 CTA (tuning; measured: no effect)
   bool fast_log10 = false;    // sa_ctx_set_fast_log10
@@ -102,6 +104,13 @@ struct sa_ctx {
   size_t slot_in_bytes = 0, slot_out_bytes = 0, slot_stats_bytes = 0;
   cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
   bool pipeline_ready = false;
+  // pageable callers: pinned staging ring (one block per pipeline slot and direction) instead of page-locking the
+  // caller's whole buffers for the call (measured 5x slower than pinned buffers: cudaHostRegister of gigabytes)
+  unsigned char *pin_in[kSlots] = {nullptr, nullptr, nullptr};
+  unsigned char *pin_out[kSlots] = {nullptr, nullptr, nullptr};
+  unsigned char *pin_st[kSlots] = {nullptr, nullptr, nullptr};
+  size_t pin_in_bytes = 0, pin_out_bytes = 0, pin_st_bytes = 0;
+  bool host_register = false;   // SA_HOST_PIN=register: the old behaviour (A/B testing)
   // single-frame call (sa_spectrum_single): one pinned host block and one device block, reused
   unsigned char *single_pin = nullptr, *single_dev = nullptr;
   size_t single_bytes = 0;
@@ -158,6 +167,7 @@ int launch_cfg(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
   const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
   kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(p);
   ctx->launches++;
+  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel<SpectrumCfg<%d,%d,%d>>", log2n, C::E, C::FPB);
   SA_CUDA(cudaGetLastError());
   return SA_OK;
 }
@@ -208,6 +218,7 @@ int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
   const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
   kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(P);
   ctx->launches++;
+  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_v2<V2Cfg<%d,%d,0>,%d,%d>", C::LOG2N, C::G, MODE, FULL ? 1 : 0);
   SA_CUDA(cudaGetLastError());
   return SA_OK;
 }
@@ -229,6 +240,7 @@ int launch_v3_inst(sa_ctx *ctx, const V2Params &P) {
   const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
   kernel<<<grid, C::NT_ALL, C::SMEM_TOTAL, ctx->stream>>>(P);
   ctx->launches++;
+  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_v3<V2Cfg<%d,%d,%d>,%d,%d>", C::LOG2N, C::G, C::NSW, MODE, FULL ? 1 : 0);
   SA_CUDA(cudaGetLastError());
   return SA_OK;
 }
@@ -327,6 +339,7 @@ int launch_small_inst(sa_ctx *ctx, const V2Params &P) {
   const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
   kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(P);
   ctx->launches++;
+  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_small<SmallCfg<%d>,%d,%d>", C::LOG2N, MODE, FULL ? 1 : 0);
   SA_CUDA(cudaGetLastError());
   return SA_OK;
 }
@@ -371,6 +384,7 @@ int launch_spectrum(sa_ctx *ctx, const SpectrumParams &p, int log2n) {
       const unsigned grid = (unsigned)((p.n_frames + 127) / 128);
       spectrum_tiny_kernel<<<grid, 128, 0, ctx->stream>>>(p, log2n);
       ctx->launches++;
+      snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_tiny_kernel");
       SA_CUDA(cudaGetLastError());
       return SA_OK;
     }
@@ -466,6 +480,50 @@ int ensure_pipeline(sa_ctx *ctx, size_t in_bytes, size_t out_bytes, size_t stats
   return SA_OK;
 }
 
+// memcpy split over a few host threads (a single thread moves ~10 GB/s, PCIe Gen5 x16 ~55 GB/s)
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  static const unsigned nthreads = [] {
+    const char *e = getenv("SA_HOST_COPY_THREADS");
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    return e ? (unsigned)std::max(1, atoi(e)) : std::min(8u, std::max(1u, hw / 2));
+  }();
+  if (bytes < (8u << 20) || nthreads == 1) { std::memcpy(dst, src, bytes); return; }
+  const size_t part = ((bytes / nthreads) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nthreads; t++) {
+    const size_t off = (size_t)t * part;
+    if (off >= bytes) break;
+    th.emplace_back([=] { std::memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, std::min(part, bytes - off)); });
+  }
+  std::memcpy(dst, src, std::min(part, bytes));
+  for (auto &t : th) t.join();
+}
+
+bool is_cuda_host_memory(const void *p) {
+  cudaPointerAttributes a;
+  const bool yes = cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type != cudaMemoryTypeUnregistered;
+  (void)cudaGetLastError();
+  return yes;
+}
+
+int ensure_staging(sa_ctx *ctx, bool in, size_t in_bytes, bool out, size_t out_bytes, bool st, size_t st_bytes) {
+  auto grow = [&](unsigned char *(&blk)[sa_ctx::kSlots], size_t &have, size_t need) -> int {
+    if (have >= need) return SA_OK;
+    for (int s = 0; s < sa_ctx::kSlots; s++) {
+      if (blk[s]) SA_CUDA(cudaFreeHost(blk[s]));
+      blk[s] = nullptr;
+      SA_CUDA(cudaMallocHost(&blk[s], need));
+    }
+    have = need;
+    return SA_OK;
+  };
+  int e;
+  if (in && (e = grow(ctx->pin_in, ctx->pin_in_bytes, in_bytes)) != SA_OK) return e;
+  if (out && (e = grow(ctx->pin_out, ctx->pin_out_bytes, out_bytes)) != SA_OK) return e;
+  if (st && (e = grow(ctx->pin_st, ctx->pin_st_bytes, st_bytes)) != SA_OK) return e;
+  return SA_OK;
+}
+
 // Page-locks a caller buffer for the duration of a call unless it already is CUDA host memory.
 struct ScopedPin {
   void *ptr = nullptr;
@@ -536,6 +594,8 @@ int sa_ctx_create_on_stream(int device, void *cuda_stream, sa_ctx **out_ctx) {
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   const char *fg = getenv("SA_FORCE_GENERIC");
   ctx->use_generic = fg && fg[0] == '1';
+  const char *hp = getenv("SA_HOST_PIN");
+  ctx->host_register = hp && std::string(hp) == "register";
   const char *ns = getenv("SA_SPLIT");
   ctx->split = ns && ns[0] == '1';
   if (const char *st = getenv("SA_STAGGER_NS")) ctx->stagger_ns = (unsigned)strtoul(st, nullptr, 10);
@@ -567,6 +627,11 @@ int sa_ctx_destroy(sa_ctx *ctx) {
     if (ctx->pipeline_ready) { cudaEventDestroy(ctx->ev_h2d[s]); cudaEventDestroy(ctx->ev_comp[s]); cudaEventDestroy(ctx->ev_d2h[s]); }
   }
   if (ctx->pipeline_ready) { cudaStreamDestroy(ctx->h2d); cudaStreamDestroy(ctx->d2h); }
+  for (int s = 0; s < sa_ctx::kSlots; s++) {
+    if (ctx->pin_in[s]) cudaFreeHost(ctx->pin_in[s]);
+    if (ctx->pin_out[s]) cudaFreeHost(ctx->pin_out[s]);
+    if (ctx->pin_st[s]) cudaFreeHost(ctx->pin_st[s]);
+  }
   if (ctx->single_pin) cudaFreeHost(ctx->single_pin);
   if (ctx->single_dev) cudaFree(ctx->single_dev);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -587,6 +652,8 @@ int sa_ctx_sync(sa_ctx *ctx) {
 }
 
 uint64_t sa_ctx_launch_count(const sa_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+const char *sa_ctx_last_kernel(const sa_ctx *ctx) { return ctx ? ctx->last_kernel : ""; }
 
 int sa_window_coeffs(int window_kind, uint32_t n, float *host_out) {
   if (!host_out || window_kind < SA_WINDOW_NONE || window_kind > SA_WINDOW_BLACKMAN_HARRIS_7TERM || n > 32768)
@@ -628,6 +695,13 @@ static int spectrum_batched_impl(sa_ctx *ctx, const void *d_samples, int in_i16,
   if (n_frames == 0) return SA_OK;
   if (!d_samples || !d_out_vals || out_stride < nb || frame_stride == 0) return SA_ERR_INVALID_ARGUMENT;
   if ((stats_mask & SA_STATS_ALL) && !d_stats) return SA_ERR_INVALID_ARGUMENT;
+  // natural alignment of the element types (a misaligned pointer would fault inside the kernel)
+  if (reinterpret_cast<uintptr_t>(d_samples) % (in_i16 ? alignof(int16_t) : alignof(float)) != 0 ||
+      reinterpret_cast<uintptr_t>(d_out_vals) % alignof(float) != 0 ||
+      ((stats_mask & SA_STATS_ALL) && reinterpret_cast<uintptr_t>(d_stats) % 16 != 0)) {
+    g_last_error = "misaligned pointer: samples need their element alignment, values 4 bytes, records 16 bytes";
+    return SA_ERR_INVALID_ARGUMENT;
+  }
   SA_CUDA(cudaSetDevice(ctx->device));
   SpectrumParams p;
   int pe = fill_params(ctx, p, d_samples, in_i16, n_frames, n, frame_stride, window_kind, scaling_kind, stats_mask,
@@ -671,6 +745,11 @@ static int spectrum_batched_host_impl(sa_ctx *ctx, const void *h_samples_v, int 
   if (!h_samples || !h_out_vals || out_stride < nb || frame_stride == 0) return SA_ERR_INVALID_ARGUMENT;
   const bool want_stats = (stats_mask & SA_STATS_ALL) != 0;
   if (want_stats && !h_stats) return SA_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(h_samples) % esz != 0 || reinterpret_cast<uintptr_t>(h_out_vals) % alignof(float) != 0 ||
+      (want_stats && reinterpret_cast<uintptr_t>(h_stats) % alignof(uint32_t) != 0)) {
+    g_last_error = "misaligned host pointer";
+    return SA_ERR_INVALID_ARGUMENT;
+  }
   SA_CUDA(cudaSetDevice(ctx->device));
 
   // chunking: ~64 MiB of unique input per chunk
@@ -684,10 +763,37 @@ static int spectrum_batched_host_impl(sa_ctx *ctx, const void *h_samples_v, int 
   int pe = ensure_pipeline(ctx, in_bytes, out_bytes, st_bytes);
   if (pe != SA_OK) return pe;
 
+  // Declared BEFORE the pins: on every exit path (errors included) the three streams are drained first, so no copy
+  // into or out of the caller's buffers is in flight when the buffers are unpinned and handed back.
+  struct Drain {
+    sa_ctx *c;
+    ~Drain() { cudaStreamSynchronize(c->d2h); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->h2d); }
+  };
   ScopedPin pin_in, pin_out, pin_st;
-  pin_in.pin(h_samples, ((n_frames - 1) * frame_stride + n) * esz);
-  pin_out.pin(h_out_vals, ((n_frames - 1) * out_stride + nb) * sizeof(float));
-  if (want_stats) pin_st.pin(h_stats, n_frames * sizeof(sa_frame_stats));
+  Drain drain{ctx};   // destroyed first (reverse order of declaration)
+  // Pageable caller memory goes through a pinned staging ring (host threads copy a chunk while the previous ones
+  // are on the bus); memory that already is CUDA host memory is used in place.
+  bool stage_in = false, stage_out = false, stage_st = false;
+  if (ctx->host_register) {
+    pin_in.pin(h_samples, ((n_frames - 1) * frame_stride + n) * esz);
+    pin_out.pin(h_out_vals, ((n_frames - 1) * out_stride + nb) * sizeof(float));
+    if (want_stats) pin_st.pin(h_stats, n_frames * sizeof(sa_frame_stats));
+  } else {
+    stage_in = in_bytes >= (1u << 20) && !is_cuda_host_memory(h_samples);
+    stage_out = out_bytes >= (1u << 20) && !is_cuda_host_memory(h_out_vals);
+    stage_st = want_stats && stage_out && !is_cuda_host_memory(h_stats);
+    pe = ensure_staging(ctx, stage_in, in_bytes, stage_out, out_bytes, stage_st, st_bytes);
+    if (pe != SA_OK) return pe;
+  }
+  // staged outputs of chunk number `cc` (slot cc % kSlots): wait for its D2H copies, then hand the rows to the caller
+  auto deliver = [&](uint64_t cc) -> int {
+    const int sl = (int)(cc % sa_ctx::kSlots);
+    const uint64_t g0 = cc * chunk, gn = std::min(chunk, n_frames - g0);
+    SA_CUDA(cudaEventSynchronize(ctx->ev_d2h[sl]));
+    if (stage_out) parallel_memcpy(h_out_vals + g0 * out_stride, ctx->pin_out[sl], ((gn - 1) * out_stride + nb) * sizeof(float));
+    if (stage_st) std::memcpy(h_stats + g0, ctx->pin_st[sl], gn * sizeof(sa_frame_stats));
+    return SA_OK;
+  };
 
   const int log2n = log2_exact(n);
   uint64_t c = 0;
@@ -695,11 +801,18 @@ static int spectrum_batched_host_impl(sa_ctx *ctx, const void *h_samples_v, int 
     const int s = (int)(c % sa_ctx::kSlots);
     const uint64_t nf = std::min(chunk, n_frames - f0);
     if (c >= (uint64_t)sa_ctx::kSlots) {
+      if (stage_out && (pe = deliver(c - sa_ctx::kSlots)) != SA_OK) return pe;   // frees this slot's staged outputs
       SA_CUDA(cudaStreamWaitEvent(ctx->h2d, ctx->ev_comp[s], 0));     // input slot consumed
       SA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));   // output slot drained
     }
-    SA_CUDA(cudaMemcpyAsync(ctx->slot_in[s], h_samples + f0 * frame_stride * esz,
-                            ((nf - 1) * frame_stride + n) * esz, cudaMemcpyHostToDevice, ctx->h2d));
+    const unsigned char *src = h_samples + f0 * frame_stride * esz;
+    const size_t src_bytes = ((nf - 1) * frame_stride + n) * esz;
+    if (stage_in) {
+      if (c >= (uint64_t)sa_ctx::kSlots) SA_CUDA(cudaEventSynchronize(ctx->ev_h2d[s]));   // the block's previous copy has left
+      parallel_memcpy(ctx->pin_in[s], src, src_bytes);
+      src = ctx->pin_in[s];
+    }
+    SA_CUDA(cudaMemcpyAsync(ctx->slot_in[s], src, src_bytes, cudaMemcpyHostToDevice, ctx->h2d));
     SA_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->h2d));
     SA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
     SpectrumParams p;
@@ -710,13 +823,16 @@ static int spectrum_batched_host_impl(sa_ctx *ctx, const void *h_samples_v, int 
     if (pe != SA_OK) return pe;
     SA_CUDA(cudaEventRecord(ctx->ev_comp[s], ctx->stream));
     SA_CUDA(cudaStreamWaitEvent(ctx->d2h, ctx->ev_comp[s], 0));
-    SA_CUDA(cudaMemcpyAsync(h_out_vals + f0 * out_stride, ctx->slot_out[s],
+    SA_CUDA(cudaMemcpyAsync(stage_out ? reinterpret_cast<float *>(ctx->pin_out[s]) : h_out_vals + f0 * out_stride, ctx->slot_out[s],
                             ((nf - 1) * out_stride + nb) * sizeof(float), cudaMemcpyDeviceToHost, ctx->d2h));
     if (want_stats)
-      SA_CUDA(cudaMemcpyAsync(h_stats + f0, ctx->slot_stats[s], nf * sizeof(sa_frame_stats),
-                              cudaMemcpyDeviceToHost, ctx->d2h));
+      SA_CUDA(cudaMemcpyAsync(stage_st ? reinterpret_cast<sa_frame_stats *>(ctx->pin_st[s]) : h_stats + f0, ctx->slot_stats[s],
+                              nf * sizeof(sa_frame_stats), cudaMemcpyDeviceToHost, ctx->d2h));
     SA_CUDA(cudaEventRecord(ctx->ev_d2h[s], ctx->d2h));
   }
+  if (stage_out)   // the last (up to kSlots) chunks are still in the staging blocks
+    for (uint64_t cc = c > (uint64_t)sa_ctx::kSlots ? c - sa_ctx::kSlots : 0; cc < c; cc++)
+      if ((pe = deliver(cc)) != SA_OK) return pe;
   SA_CUDA(cudaStreamSynchronize(ctx->d2h));
   SA_CUDA(cudaStreamSynchronize(ctx->stream));
   SA_CUDA(cudaStreamSynchronize(ctx->h2d));

@@ -316,6 +316,13 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
   // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
+#ifndef SA_OPT
+#define SA_OPT 0   // experiments, both off.  bit 0: packed window multiply (+1.4 % at cfg2, but ptxas contracts it into the first
+                   // butterflies, so the fused window stops being bit-identical to a caller-side window: rejected);
+                   // bit 1: scaling folded into the window table (no gain)
+#endif
+  constexpr bool FOLD_SCALE = (MODE == SCALE_MUL) && (SA_OPT & 2);
+  const float wscale = FOLD_SCALE ? P.cmul : 1.0f;
   const int jbB = j ? 256 - j : 128;   // MIRROR: second last-pass butterfly of this thread
   // N = 8192 (neither MIRROR nor MIRG): butterfly of this thread in the last pass
   const int beta = (j & 31) < 16 ? 16 * (j >> 5) + (j & 31)
@@ -332,7 +339,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
         for (int s = 0; s < 8; s++) {
           const float2 w = has_win ? __ldg(reinterpret_cast<const float2 *>(p.window) + j + (8 * h + s) * T) : make_float2(1.f, 1.f);
-          v[2 * s] = w.x; v[2 * s + 1] = w.y;
+          // SCALE_MUL: the scaling factor (a power of two: 1/2 of the real-FFT recombination times 1/N or 1/sqrt(N))
+          // rides on the window multipliers -- everything downstream is linear and a power of two commutes with
+          // every rounding, so the values are the same bits as scaling at the end
+          v[2 * s] = w.x * wscale; v[2 * s + 1] = w.y * wscale;
         }
         tmem_st16(ta + C::TM_WIN + 16 * h, v);
       }
@@ -414,11 +424,15 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
   // ---- load of the first frame (raw samples; the window is applied at the top of the loop) ------
   float2 x[E];
-  // Byte address of frame f.  Bulk copies need 16-byte aligned addresses and sizes: the copy fetches the
-  // aligned superset [addr & ~15, round_up_16(addr + frame bytes)) and the frame sits `addr & 15` bytes into
-  // the staging buffer.  (The superset stays inside the 256-byte granules CUDA allocations are made of.)
+  // Byte address of frame f.  Bulk copies need 16-byte aligned addresses and sizes: a frame that does not start on
+  // a 16-byte boundary is fetched as its aligned superset [addr & ~15, round_up_16(addr + frame bytes)) and sits
+  // `addr & 15` bytes into the staging buffer.  Where that superset would leave the caller's buffer
+  // [samples, samples + extent) -- the first bytes of the first frame, the last bytes of the last one -- the copy is
+  // clamped to the aligned interior and the (at most 15) bytes on that side are copied by ordinary loads: nothing
+  // outside the buffer is ever read.
   const uint32_t esz = p.in_i16 ? 2u : 4u;
   const uintptr_t base_addr = reinterpret_cast<uintptr_t>(p.samples);
+  const uintptr_t end_addr = base_addr + ((p.n_frames - 1) * p.frame_stride + (u64)N) * esz;
   auto frame_addr = [&](u64 f) -> uintptr_t { return base_addr + f * p.frame_stride * esz; };
   // thread 0 of the group: bulk copy of frame f into the staging buffer
   const bool al16 = p.aligned16 != 0;   // launch-uniform: every frame starts on a 16-byte boundary
@@ -431,10 +445,26 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       mbar_arrive_expect_tx(mbar, (uint32_t)N * esz);
       bulk_copy_g2s(stage, reinterpret_cast<const void *>(a), (uint32_t)N * esz, mbar);
     } else {
-      const uintptr_t a0 = a & ~(uintptr_t)15;
-      const uint32_t bytes = (uint32_t)(((a - a0) + (uintptr_t)N * esz + 15u) & ~(uintptr_t)15);
-      mbar_arrive_expect_tx(mbar, bytes);
-      bulk_copy_g2s(stage, reinterpret_cast<const void *>(a0), bytes, mbar);
+      const uintptr_t fe = a + (uintptr_t)N * esz;                 // end of the frame
+      uintptr_t a0 = a & ~(uintptr_t)15, a1 = (fe + 15u) & ~(uintptr_t)15;
+      const uintptr_t s0 = a0;                                     // address that maps to stage[0]
+      if (a0 < base_addr) {                                        // head of the first frame: ordinary loads
+        a0 += 16;
+        for (uintptr_t q = a; q < a0; q += esz) {
+          if (esz == 4u) *reinterpret_cast<float *>(stage + (q - s0)) = *reinterpret_cast<const float *>(q);
+          else *reinterpret_cast<short *>(stage + (q - s0)) = *reinterpret_cast<const short *>(q);
+        }
+      }
+      if (a1 > end_addr) {                                         // tail of the last frame
+        a1 -= 16;
+        for (uintptr_t q = a1 > a ? a1 : a; q < fe; q += esz) {
+          if (esz == 4u) *reinterpret_cast<float *>(stage + (q - s0)) = *reinterpret_cast<const float *>(q);
+          else *reinterpret_cast<short *>(stage + (q - s0)) = *reinterpret_cast<const short *>(q);
+        }
+      }
+      const uint32_t bytes = (uint32_t)(a1 - a0);
+      mbar_arrive_expect_tx(mbar, bytes);    // (release: the ordinary stores above are visible to the waiters)
+      bulk_copy_g2s(stage + (a0 - s0), reinterpret_cast<const void *>(a0), bytes, mbar);
     }
   };
   if (j == 0) stage_frame(frame);
@@ -503,8 +533,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       tmem_ld32(ta + C::TM_WIN, w);
 #pragma unroll
       for (int s = 0; s < E; s++) {
-        x[s].x = __fmul_rn(w[2 * s], x[s].x);
-        x[s].y = __fmul_rn(w[2 * s + 1], x[s].y);
+        if constexpr (SA_OPT & 1) {
+          x[s] = mul2(make_float2(w[2 * s], w[2 * s + 1]), x[s]);
+        } else {
+          x[s].x = __fmul_rn(w[2 * s], x[s].x);
+          x[s].y = __fmul_rn(w[2 * s + 1], x[s].y);
+        }
       }
     }
 
@@ -813,7 +847,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       else if constexpr (MODE == SCALE_ZERO_ONE) return umax != 0.0f ? __fdiv_rn(v, umax) : 0.0f;
       else return (v == 0.0f) ? 0.0f : __fmul_rn(20.0f, log10f_musl(v));
     };
-    if constexpr (MODE == SCALE_MUL) {
+    if constexpr (FOLD_SCALE) {
+      // already scaled (the factor rides on the window multipliers)
+    } else if constexpr (MODE == SCALE_MUL) {
 #pragma unroll
       for (int i = 0; i < E; i += 2) {
         const float2 r = mul2(make_float2(val[i], val[i + 1]), bcast2(cscale));
@@ -842,7 +878,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       for (int i = 0; i < E; i++) val[i] = scale1(val[i]);
       vmid = scale1(vmid);
     }
-    if constexpr (MODE == SCALE_MUL) vmid = scale1(vmid);
+    if constexpr (MODE == SCALE_MUL && !FOLD_SCALE) vmid = scale1(vmid);
 
     if constexpr (C::SPLIT) {
       // ---- hand-over to the group's statistics warp (sa_spectrum_v3.cuh) -----------------------------

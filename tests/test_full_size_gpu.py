@@ -142,3 +142,26 @@ def test_cfg4_large_n_range_limit(gpu_ctx):
     _check_sampled_frames(torch, x, r7, 1024, n, n, O.WINDOW_BH4, (O.LIMIT_RANGE, 50.0, 15000.0), O.SCALING_ZERO_TO_ONE,
                           [0, 511, 1023])
     assert torch.equal(r7.vals, r.vals[:1024])
+
+
+@pytest.mark.parametrize("dtype,hop", [("f32", 4096), ("i16", 1000)])
+def test_pageable_host_buffers_through_the_staging_ring(gpu_ctx, dtype, hop):
+    """sa_spectrum_batched_host from plain (pageable) numpy arrays: more chunks than pipeline slots, so every staging
+    block is reused; values and records must equal the device-resident call bit for bit."""
+    import numpy as np
+    import torch
+    import spectrum_analyzer_b200 as sa
+    n, frames = 4096, 30_011 if hop == 4096 else 90_017
+    rng = np.random.default_rng(8)
+    if dtype == "f32":
+        x = rng.standard_normal((frames - 1) * hop + n).astype(np.float32)
+    else:
+        x = rng.integers(-32768, 32767, (frames - 1) * hop + n).astype(np.int16)
+    lim = sa.FrequencyLimit.Range(100.0, 18000.0)
+    host = sa.samples_fft_to_spectrum_batched(x, 44100, lim, sa.scaling.scale_20_times_log10, window="hann", n=n,
+                                              frame_stride=hop, n_frames=frames)
+    dev = sa.samples_fft_to_spectrum_batched(torch.from_numpy(x).cuda(), 44100, lim, sa.scaling.scale_20_times_log10,
+                                             window="hann", n=n, frame_stride=hop, n_frames=frames)
+    torch.cuda.synchronize()
+    assert np.array_equal(host.vals.view(np.uint32), dev.vals.cpu().numpy().view(np.uint32))
+    assert np.array_equal(host.stats.view(np.uint8), dev.stats.cpu().numpy().view(np.uint8).reshape(-1))
