@@ -17,8 +17,11 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="scale the frame counts")
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=0, help="timed launches per config (0: as many as fill ~0.3 s)")
+    ap.add_argument("--only", default="", help="substring filter on the config name")
     args = ap.parse_args()
+    import time
+    from bench import ClockSampler
     import torch
     import spectrum_analyzer_b200 as sa
     from spectrum_analyzer_b200 import cabi
@@ -61,6 +64,8 @@ def main():
         ("i16 cfg3 2048 hamming hop512", 2048, 512, 775_000, cabi.WINDOW_HAMMING, L.All, cabi.SCALING_NONE, 7),
     ]
     for name, n, hop, frames, win, lim, sc, st in configs:
+        if args.only and args.only not in name:
+            continue
         i16 = name.startswith("i16")
         chk(lib.sa_ctx_set_fast_log10(ctx._h, 1 if name.startswith("fastlog") else 0))
         frames = max(1024, int(frames * args.scale))
@@ -81,19 +86,36 @@ def main():
         for _ in range(3):
             step()
         torch.cuda.synchronize()
+        # size the timed region (>= 0.3 s) so that the 50 ms clock sampler sees it
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        steps = args.steps or max(5, int(300.0 / max(e0.elapsed_time(e1), 1e-3)) + 1)
+        sampler = ClockSampler(0)
+        sampler.start()
+        time.sleep(0.12)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
             step()
         e1.record(stream)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        t1 = time.perf_counter()
+        clocks = sampler.stop(t0, t1)
+        ms = e0.elapsed_time(e1) / steps
         bpf = esz * hop + 4 * n_bins + 32
         fps = frames / (ms * 1e-3)
         ok = int((stats.view(torch.int32).view(frames, 8)[:, 6] != 0).sum().item()) == 0
         print(json.dumps({"config": name, "n": n, "hop": hop, "frames": frames, "n_bins": n_bins, "ms": round(ms, 4),
                           "frames_per_s": fps, "msamples_per_s": fps * hop / 1e6, "algorithmic_bytes_per_frame": bpf,
                           "achieved_gbs": bpf * fps / 1e9, "hbm_frac_of_measured": bpf * fps / 1e9 / peak,
+                          # roofline ridge of the path at this N (north_star): ~5 N log2 N flop per frame over the
+                          # algorithmic bytes; B200 fp32 ridge = 75 TFLOP/s (non-tensor) / measured HBM = ~11.5 flop/B
+                          "flop_per_byte": 2.5 * n * (n.bit_length() - 1) / bpf,
+                          "fp32_tflops_algorithmic": 2.5 * n * (n.bit_length() - 1) * fps / 1e12,
+                          "kernel": ctx.last_kernel, "steps": steps, "clocks": clocks,
                           "all_status_ok": ok}), flush=True)
         del x, vals, stats
         torch.cuda.empty_cache()

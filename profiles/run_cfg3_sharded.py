@@ -31,7 +31,7 @@ N, HOP, SR, SEED, K = 2048, 512, 44100, 0xC0FFEE, 8
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hours", type=float, default=10.0)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=0, help="0: as many as fill ~0.3 s")
     ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
     import numpy as np
@@ -76,6 +76,17 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if args.steps <= 0:     # size the timed region so that the 50 ms clock sampler sees it (same count on every rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        args.steps = max(5, int(300.0 / max(float(t.item()), 1e-3)) + 1)
+        barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.1)
@@ -121,6 +132,9 @@ def main():
         flag = torch.tensor([1 if seams_ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         seams_ok = bool(flag.item())
+        cnt = torch.tensor([seam_frames], device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        seam_frames = int(cnt.item())
 
     # ---- oracle check (rank 0's shard: first frames, last frames) ------------------------------------------------
     oracle = None
@@ -153,7 +167,7 @@ def main():
             "halo_samples": N - HOP, "steps": args.steps, "ms_per_step": ms / args.steps, "frames_per_s": value,
             "msamples_per_s": value * HOP / 1e6, "kernel": ctx.last_kernel,
             "hbm_frac_unique_bytes": value * unique_bytes / 1e9 / (peak * world), "algorithmic_bytes_per_frame": unique_bytes,
-            "seams_bit_identical": seams_ok, "seam_frames_checked_per_rank": seam_frames, "oracle": oracle, "clocks": clocks}))
+            "seams_bit_identical": seams_ok, "seam_frames_checked_all_ranks": seam_frames, "oracle": oracle, "clocks": clocks}))
         assert seams_ok, "frames at a shard seam differ from the single-launch result"
     if world > 1:
         dist.destroy_process_group()

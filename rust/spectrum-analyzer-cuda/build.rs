@@ -19,8 +19,9 @@ fn main() {
     assert!(status.success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=spectrum_analyzer_cuda");
-    for f in ["sa_lib.cu", "sa_spectrum_v2.cuh", "sa_spectrum_kernel.cuh", "sa_aux_kernels.cuh", "sa_dft.cuh",
-              "sa_common.cuh", "sa_host_math.h"] {
+    println!("cargo:rustc-link-lib=dylib=cudart");   // src/device.rs owns device buffers and streams
+    for f in ["sa_lib.cu", "sa_spectrum_v2.cuh", "sa_spectrum_v3.cuh", "sa_spectrum_small.cuh", "sa_spectrum_kernel.cuh",
+              "sa_aux_kernels.cuh", "sa_dft.cuh", "sa_tmem.cuh", "sa_common.cuh", "sa_host_math.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", repo.join("include/spectrum_analyzer_cuda.h").display());

@@ -22,7 +22,12 @@ pub struct sa_frame_stats {
 }
 
 pub const SA_OK: c_int = 0;
+pub const SA_ERR_SCALING: u32 = 9;
 pub const SA_STATS_ALL: u32 = 7;
+pub const SA_SCALING_ERR_INDEX_MASK: u32 = 0x0000_ffff;
+pub const SA_SCALING_ERR_NAN: u32 = 0x8000_0000;
+pub const SA_SCALING_ERR_POS_INF: u32 = 0x4000_0000;
+pub const SA_SCALING_ERR_NEG_INF: u32 = 0x2000_0000;
 
 extern "C" {
     pub fn sa_abi_version() -> u32;

@@ -9,6 +9,7 @@
 //! let hann = windows::hann_window(&ctx, &samples)?;
 //! let spectrum = samples_fft_to_spectrum(&ctx, &hann, 44100, FrequencyLimit::All, Some(scaling::divide_by_N_sqrt))?;
 //! ```
+pub mod device;
 pub mod ffi;
 
 use core::ffi::c_int;
@@ -109,7 +110,15 @@ impl Context {
         if e != ffi::SA_OK { return Err(map_err(e, FrequencyLimit::All)); }
         Ok(Self { raw })
     }
+    /// A context that launches on a caller-owned stream (see `device::Stream`).
+    pub fn on_stream(device: i32, stream: &device::Stream) -> Result<Self, SpectrumAnalyzerError> {
+        let mut raw = ptr::null_mut();
+        let e = unsafe { ffi::sa_ctx_create_on_stream(device, stream.as_raw(), &mut raw) };
+        if e != ffi::SA_OK { return Err(map_err(e, FrequencyLimit::All)); }
+        Ok(Self { raw })
+    }
     pub fn sync(&self) { unsafe { ffi::sa_ctx_sync(self.raw); } }
+    pub(crate) fn raw(&self) -> *mut ffi::sa_ctx { self.raw }
 }
 impl Drop for Context {
     fn drop(&mut self) { unsafe { ffi::sa_ctx_destroy(self.raw); } }
@@ -149,7 +158,14 @@ impl FrequencySpectrum {
                                              ffi::SA_STATS_ALL, &mut self.stats)
         };
         if e != ffi::SA_OK { return Err(map_err(e, FrequencyLimit::All)); }
-        for (p, v) in self.data.iter_mut().zip(vals) { p.1 = v; }
+        // the values in front of an offender are replaced, like the reference's in-place loop (src/spectrum.rs:150-163)
+        for (p, v) in self.data.iter_mut().zip(vals.iter()) { p.1 = *v; }
+        if self.stats.status == ffi::SA_ERR_SCALING {
+            let r = self.stats.reserved;
+            let new = if r & ffi::SA_SCALING_ERR_NAN != 0 { f32::NAN }
+                      else if r & ffi::SA_SCALING_ERR_POS_INF != 0 { f32::INFINITY } else { f32::NEG_INFINITY };
+            return Err(SpectrumAnalyzerError::ScalingError(vals[(r & ffi::SA_SCALING_ERR_INDEX_MASK) as usize], new));
+        }
         Ok(())
     }
 }

@@ -330,7 +330,7 @@ int launch_small_inst(sa_ctx *ctx, const V2Params &P) {
     // The occupancy calculator answers 1 for kernels that allocate tensor memory; two CTAs of 256 threads
     // (<= 128 registers by __launch_bounds__, 48 KB of shared memory, 128 of 512 TMEM columns each) do fit.
     // The grid is persistent (frames strided by gridDim), so a CTA that had to wait would still be correct.
-    per_sm = std::max(per_sm, 2);
+    per_sm = std::max(per_sm, SA_SMALL_CTAS);
     plan.max_blocks = per_sm * ctx->num_sms;
     plan.ready = true;
   }

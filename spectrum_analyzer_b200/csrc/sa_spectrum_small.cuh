@@ -505,8 +505,11 @@ __device__ __forceinline__ void spectrum_body_small(const V2Params &P, unsigned 
   }
 }
 
+#ifndef SA_SMALL_CTAS
+#define SA_SMALL_CTAS 2   // resident CTAs per SM the register budget is sized for (2: <= 128 registers)
+#endif
 template <class C, int MODE, bool FULL>
-__global__ void __launch_bounds__(C::NT, 2) spectrum_kernel_small(const V2Params P) {
+__global__ void __launch_bounds__(C::NT, SA_SMALL_CTAS) spectrum_kernel_small(const V2Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t *slot = reinterpret_cast<uint32_t *>(smem + C::OFF_TMSLOT);
   if (threadIdx.x < 32) tmem_alloc<C::TM_COLS>(slot);

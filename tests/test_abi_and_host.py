@@ -58,6 +58,61 @@ def test_window_multipliers_bit_exact(cuda_lib, kind, n):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+def _f32_neighbours(c):
+    """c - 1 ulp, c, c + 1 ulp as float32 arrays."""
+    c = np.asarray(c, np.float32)
+    return np.nextafter(c, np.float32(-np.inf)), c, np.nextafter(c, np.float32(np.inf))
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("n", [2, 3, 8, 100, 256, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_window_multipliers_against_an_independent_cos(cuda_lib, kind, n):
+    """The product's `cosf` restatement and the oracle's are two readings of the same musl source by the same author;
+    comparing them with each other cannot catch a shared misreading.  Independent witness: libm's cosf is documented to
+    be within 1 ulp, so for the exact f32 argument the reference forms (src/windows.rs:44-46, 66) the multiplier must
+    be one of the three values obtained from the correctly rounded cosine (numpy float64 cos, rounded once) and its two
+    f32 neighbours -- and almost always the middle one."""
+    got = np.zeros(n, np.float32)
+    assert cuda_lib.sa_window_coeffs(kind, n, got.ctypes.data) == 0
+    f = np.float32
+    i = np.arange(n, dtype=np.float32)
+    two_pi = f(2.0) * f(np.pi)                                   # 2.0 * PI, one f32 product
+    if kind == 1:
+        arg = (two_pi * i).astype(np.float32) / f(n)             # (2.0 * PI * i as f32) / samples_len_f32
+        mult = lambda c: (f(0.5) * (f(1.0) - c)).astype(np.float32)
+    else:
+        arg = (two_pi * i).astype(np.float32) / (f(n) - f(1.0))
+        mult = lambda c: (f(0.54) - (f(0.46) * c).astype(np.float32)).astype(np.float32)
+    arg = arg.astype(np.float32)
+    lo, mid, hi = _f32_neighbours(np.cos(arg.astype(np.float64)).astype(np.float32))
+    cands = [mult(c).view(np.uint32) for c in (lo, mid, hi)]
+    g = got.view(np.uint32)
+    ok = (g == cands[0]) | (g == cands[1]) | (g == cands[2])
+    assert ok.all(), f"multiplier {np.nonzero(~ok)[0][:5]} outside the 1-ulp envelope of a correctly rounded cos"
+    assert (g == cands[1]).mean() >= 0.98                        # musl's cosf is correctly rounded almost everywhere
+
+
+@pytest.mark.parametrize("kind,alphas", [(3, [0.35875, -0.48829, 0.14128, -0.01168]),
+                                         (4, [0.2710514, -0.43329793, 0.218123, -0.06592545, 0.010811742,
+                                              -0.00077658484, 0.000013887217])])
+@pytest.mark.parametrize("n", [4, 100, 4096, 16384])
+def test_blackman_harris_multipliers_against_float64(cuda_lib, kind, alphas, n):
+    """Same witness for the multi-term windows (src/windows.rs:122-147): with every cosine within 1 ulp and one f32
+    rounding per multiply-add, the sum lies within sum(|alpha|) * (terms + 2) ulp(1) of the float64 value formed from
+    the same f32 arguments."""
+    got = np.zeros(n, np.float32)
+    assert cuda_lib.sa_window_coeffs(kind, n, got.ctypes.data) == 0
+    f = np.float32
+    i = np.arange(n, dtype=np.float32)
+    acc = np.zeros(n, np.float64)
+    for a, alpha in enumerate(alphas):
+        two_pi_iteration = f(2.0) * f(a) * f(np.pi)
+        arg = ((two_pi_iteration * i).astype(np.float32) / (f(n) - f(1.0))).astype(np.float32)
+        acc += float(f(alpha)) * np.cos(arg.astype(np.float64))
+    bound = sum(abs(a) for a in alphas) * (len(alphas) + 2) * 2.0 ** -23
+    assert np.abs(got.astype(np.float64) - acc).max() <= bound
+
+
 def test_window_goldens_through_the_abi(cuda_lib):
     assert np.allclose(sa.windows.coefficients("hamming", 4), [0.08, 0.77, 0.77, 0.08], atol=1e-5)          # windows.rs:156-164
     assert np.allclose(2 * sa.windows.coefficients("blackman_harris_4term", 4), [0.00012, 1.04115, 1.04115, 0.00012],
