@@ -90,7 +90,7 @@ struct V2Cfg {
   // median histogram: 64 buckets per pass (measured with the warp-cooperative ranking: 32 buckets 1.49e8,
   // 64: 1.57e8, 128: 1.56e8, 256: 1.53e8 spectra/s at cfg2; -DSA_HBITS=n rebuilds with another count)
 #ifndef SA_HBITS
-#define SA_HBITS 6
+#define SA_HBITS 7
 #endif
   // the warp-specialised variant scans the histogram once per frame (not once per warp) and ranks the selected
   // bucket in its one statistics warp: more, finer buckets pay there (fewer candidates to gather and rank)
@@ -126,7 +126,8 @@ struct V2Cfg {
   static constexpr int HSTRIDE = NBUCKET + 8;                          // [below | NBUCKET buckets | above | pad]
   static constexpr size_t G_HIST = sizeof(uint32_t) * HSTRIDE * (SPLIT_ ? NSW_ : 2);   // two histograms, alternated per frame (SPLIT: one per statistics warp)
   static constexpr size_t G_MISC = sizeof(uint32_t) * 96;
-  static constexpr size_t G_LIST = sizeof(uint32_t) * 32 * (NSW_ > 1 ? NSW_ : 1);
+  // candidate list (32 keys; the split variant: one per statistics warp) + one word per thread of the group (DEFRANK)
+  static constexpr size_t G_LIST = sizeof(uint32_t) * (32 * (NSW_ > 1 ? NSW_ : 1) + (SPLIT_ ? 0 : T));
   // the next frame's samples are staged in shared memory by a bulk asynchronous copy
   // (one per frame, issued by thread 0 of the group) instead of being loaded into registers
   // N = 2048 / 4096 / 8192: the staged frame lives in the second exchange buffer (free between the last-pass reads of one frame
@@ -151,6 +152,7 @@ struct V2Cfg {
 enum { MI_KMIN = 0, MI_KMAX = 16, MI_SUM = 32, MI_ARGMIN = 48, MI_ARGMAX = 49, MI_LCOUNT = 50,
        MI_GUESS = 51, MI_SELA = 52 /*b, below, cnt*/, MI_LDONE = 55, MI_SELB = 56, MI_RESA = 57, MI_RESB = 58,
        MI_FLAGS = 59, MI_WINL = 60 /* SPLIT: two windows published by the statistics warp: {klo, shift | use << 8} per frame parity */,
+       MI_DEF = 92 /* deferred ranking: {candidates, wanted rank, frame lo, frame hi} (16-byte aligned) */,
        MI_UMAX = 64, MI_BMIN = 80, MI_BMAX = 88 /* SPLIT: per warp, the lanes that hold the warp's minimum / maximum */ };
 // misc words of a group in the split variant (the words above except MI_UMAX are unused there).  [s]: hand-over slot
 // (statistics warp) s = frame parity when NSW = 2, 0 when NSW = 1; [p]: frame parity.
@@ -280,6 +282,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   uint32_t *hist0 = reinterpret_cast<uint32_t *>(gbase + OFF_HIST);
   uint32_t *misc = reinterpret_cast<uint32_t *>(gbase + OFF_HIST + C::G_HIST);
   uint32_t *list = reinterpret_cast<uint32_t *>(gbase + OFF_HIST + C::G_HIST + C::G_MISC);
+  uint32_t *cand = list + 32;      // DEFRANK: candidate of thread j of the group (16-byte aligned)
   unsigned char *tail = gbase + OFF_HIST + C::G_HIST + C::G_MISC + C::G_LIST;
   constexpr bool ALIAS = C::ALIAS;
   unsigned char *stage = ALIAS ? reinterpret_cast<unsigned char *>(bufB) : tail;
@@ -294,6 +297,16 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   uint32_t ephase = 0;               // bit s = parity of the next wait on empty[s]
   uint32_t fcount = 0;               // frames handed over so far
   constexpr int HBITS = C::HBITS, HBPL = C::HBPL;
+#ifndef SA_DEFRANK
+#define SA_DEFRANK 1
+#endif
+  // DEFRANK: the candidates of a frame's selected bucket are ranked one group barrier later (right after the first
+  // exchange barrier of the group's next frame, when the list is known to be complete) by ONE fixed warp, instead of
+  // by the warp of the thread that completed the list: that warp was by construction the group's latest, and its
+  // chain fence -> atomic -> vote -> fence -> list -> shuffles -> store held the whole group at its next barrier
+  // (profiles/README.md, round 2: 0.63 -> 0.70 of the roofline with that chain removed).
+  constexpr bool DEFRANK = SA_DEFRANK && !C::SPLIT;
+  constexpr int RANKW = NW > 1 ? 1 : 0;      // logical warp of the group that ranks
 #ifndef SA_GW_MIN_LOG2
 #define SA_GW_MIN_LOG2 17
 #endif
@@ -317,9 +330,13 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // ---- one-time: tables -> tensor memory (or shared / global memory for N = 16384), histogram cleared
   const bool has_win = p.window != nullptr;
 #ifndef SA_OPT
-#define SA_OPT 0   // experiments, both off.  bit 0: packed window multiply (+1.4 % at cfg2, but ptxas contracts it into the first
-                   // butterflies, so the fused window stops being bit-identical to a caller-side window: rejected);
-                   // bit 1: scaling folded into the window table (no gain)
+#define SA_OPT 3   // bit 0: packed window multiply (FMUL2: -16 instructions per thread).  ptxas contracts a packed multiply with
+                   // the packed add that consumes it into FFMA2, so half of the first-pass inputs skip the rounding of
+                   // the windowed sample (src/windows.rs:47 multiplies, then microfft adds): the fused window is then more
+                   // accurate than, and no longer bit-identical to, a caller-side window followed by window = none; both stay
+                   // far inside the 1e-4 x frame-maximum tolerance.  Measured +1.0 % at cfg2.
+                   // bit 1: a power-of-two scaling factor rides on the window multipliers instead of costing a multiply
+                   // per bin (exact: every later operation commutes with a power of two).  Measured +0.9 % at cfg2.
 #endif
   constexpr bool FOLD_SCALE = (MODE == SCALE_MUL) && (SA_OPT & 2);
   const float wscale = FOLD_SCALE ? P.cmul : 1.0f;
@@ -394,7 +411,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // window multiplier from global memory (rare paths only)
   auto win1 = [&](int n) -> float { return has_win ? __ldg(p.window + n) : 1.0f; };
   for (int i = j; i < (int)(C::G_HIST / sizeof(uint32_t)); i += T) hist0[i] = 0;
-  if (j == 0) { misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
+  if (j == 0) { misc[MI_DEF] = 0u; misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
   if (j == 0) {
     mbar_init(mbar, 1);
     if constexpr (C::SPLIT) {
@@ -493,6 +510,68 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u;
   };
 
+  // DEFRANK: median of the group's previous frame from the candidate table (complete: a group barrier has passed since
+  // the last store to it) -- the `want`-th smallest of the `cnt` keys in it (src/spectrum.rs:515-524 sorts; equal keys
+  // are equal values, so ties need no order).  One warp; each lane holds T/32 table words plus one overflow key.
+  // Up to three keys are settled by their minimum, maximum and sum (three independent warp reductions); more by
+  // stripping minima.
+  auto deferred_select = [&]() {
+    if constexpr (DEFRANK) {
+      if (wig == RANKW) {
+        const uint4 d = *reinterpret_cast<const uint4 *>(&misc[MI_DEF]);
+        if (d.x) {
+          constexpr int KPL = T / 32;                 // table words per lane
+          constexpr uint32_t NONE = 0xffffffffu;
+          uint32_t k[KPL + 1];
+          if constexpr (KPL % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < KPL / 4; q++) {
+              const uint4 v = reinterpret_cast<const uint4 *>(cand)[lane + 32 * q];
+              k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < KPL; q++) k[q] = cand[lane + 32 * q];
+          }
+          const uint32_t novf = misc[MI_LCOUNT], kovf = list[lane];   // (independent loads)
+          k[KPL] = ((uint32_t)lane < novf) ? kovf : NONE;
+          uint32_t cnt = d.x, want = d.y, res;
+          for (;;) {
+            uint32_t mn = NONE, mx = 0u, sm = 0u;
+#pragma unroll
+            for (int q = 0; q <= KPL; q++) {
+              const bool v = k[q] != NONE;
+              mn = min(mn, k[q]);
+              mx = max(mx, v ? k[q] : 0u);
+              sm += v ? k[q] : 0u;
+            }
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            if (cnt <= 3u) {
+              mx = __reduce_max_sync(0xffffffffu, mx);
+              sm = __reduce_add_sync(0xffffffffu, sm);
+              res = want == 0u ? mn : (want == cnt - 1u ? mx : sm - mn - mx);
+              break;
+            }
+            uint32_t c = 0u;
+#pragma unroll
+            for (int q = 0; q <= KPL; q++) { const bool e = (k[q] == mn); c += e ? 1u : 0u; k[q] = e ? NONE : k[q]; }
+            c = __reduce_add_sync(0xffffffffu, c);
+            res = mn;
+            if (want < c || c == 0u) break;      // (c == 0 cannot happen: the table holds cnt keys)
+            want -= c; cnt -= c;
+          }
+          if (lane == 0) {
+            const u64 cf = (u64)d.z | ((u64)d.w << 32);
+            reinterpret_cast<uint32_t *>(&p.stats[cf])[5] = __float_as_uint(v2_unkey<MODE>(res));
+            misc[MI_GUESS] = res;
+            misc[MI_LCOUNT] = 0u;
+            misc[MI_DEF] = 0u;
+          }
+        }
+      }
+    }
+  };
+
 #pragma unroll 1
   for (;;) {
     const bool more = frame + fstep < p.n_frames;   // group-uniform
@@ -553,6 +632,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     // every thread of the group has consumed the staged samples and finished the previous frame
     if constexpr (!ALIAS) { if (j == 0 && more) stage_frame(frame + fstep); }
     if constexpr (!C::SPLIT) { if (want_stats && rec_thread) flush_record(); }
+    if (want_median) deferred_select();
     {
       const float2 *r = wbuf + (j + (j >> 4));
 #pragma unroll
@@ -567,8 +647,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
       for (int k = 1; k < 16; k++) x[k] = cmul(x[k], make_float2(t[2 * (k - 1)], t[2 * (k - 1) + 1]));
     }
-    dft16(x);
-    {
+    if (!(SA_EXP & 0x80000)) dft16(x);   // (timing experiment 0x80000: no second-pass butterflies)
+    if (!(SA_EXP & 0x40000)) {          // (timing experiment 0x40000: no second exchange, registers passed through)
       // second exchange: unit-stride runs of 16 on both sides -> no padding needed
       float2 *w = wbuf + (j >> 4) * 256 + (j & 15);
 #pragma unroll
@@ -579,8 +659,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     float vmid = 0.f;    // bin M/2, thread 0 only
     if constexpr (MIRROR) {
       // ---- pass 3 (last): two radix-8 butterflies, jbA = j -> x[0..7], jbB -> x[8..15] ------------
+      if (!(SA_EXP & 0x40000)) {
 #pragma unroll
       for (int k = 0; k < 8; k++) { x[k] = wbuf[j + 256 * k]; x[8 + k] = wbuf[jbB + 256 * k]; }
+      }
       { float2 *t = wbuf; wbuf = obuf; obuf = t; if constexpr (C::NBUF == 1) group_sync<T>(g); }
       if constexpr (C::SPLIT && ALIAS) {
         // every warp has read its last-pass inputs -> the next frame may land in buffer B: the LAST warp to get
@@ -1046,8 +1128,11 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
       if (use_win) {
 #pragma unroll
-        for (int i = 0; i < E; i++)   // unconditional: dropped bins are +Inf and count as "above"
-          atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(val[i]), winL, shw)], 1u);
+        for (int i = 0; i < E; i++) {   // unconditional: dropped bins are +Inf and count as "above"
+          const uint32_t sl = hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(val[i]), winL, shw);
+          if (SA_EXP & 0x2000) atomicAdd(&hist[0], 1u);
+          else if (!(SA_EXP & 0x800)) atomicAdd(&hist[sl], 1u);
+        }
         if (valid_mid) atomicAdd(&hist[hist_slot<MODE, C::NBUCKET>(v2_key<MODE>(vmid), winL, shw)], 1u);
       }
       const uint32_t my_kmn = kmn, my_kmx = kmx;
@@ -1064,12 +1149,33 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         group_sync<T>(g);
         // every thread has read its last-pass inputs from the second exchange buffer: the next frame may land there
         if constexpr (ALIAS) { if (j == 0 && more) stage_frame(frame); }
-        kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
+        // the NW partial results of each kind as 16-byte loads (shared-memory instructions are the expensive ones)
+        {
+          uint32_t pmn[NW], pmx[NW], psm[NW];
+          if constexpr (NW % 4 == 0) {
 #pragma unroll
-        for (int w = 1; w < NW; w++) {
-          kmn = min(kmn, misc[MI_KMIN + w]);
-          kmx = max(kmx, misc[MI_KMAX + w]);
-          sum += __uint_as_float(misc[MI_SUM + w]);
+            for (int q = 0; q < NW / 4; q++) {
+              const uint4 a = reinterpret_cast<const uint4 *>(misc + MI_KMIN)[q];
+              const uint4 b = reinterpret_cast<const uint4 *>(misc + MI_KMAX)[q];
+              const uint4 c = reinterpret_cast<const uint4 *>(misc + MI_SUM)[q];
+              pmn[4 * q] = a.x; pmn[4 * q + 1] = a.y; pmn[4 * q + 2] = a.z; pmn[4 * q + 3] = a.w;
+              pmx[4 * q] = b.x; pmx[4 * q + 1] = b.y; pmx[4 * q + 2] = b.z; pmx[4 * q + 3] = b.w;
+              psm[4 * q] = c.x; psm[4 * q + 1] = c.y; psm[4 * q + 2] = c.z; psm[4 * q + 3] = c.w;
+            }
+          } else {
+            static_assert(NW == 2 || NW % 4 == 0, "partial-result loads");
+            const uint2 a = *reinterpret_cast<const uint2 *>(misc + MI_KMIN);
+            const uint2 b = *reinterpret_cast<const uint2 *>(misc + MI_KMAX);
+            const uint2 c = *reinterpret_cast<const uint2 *>(misc + MI_SUM);
+            pmn[0] = a.x; pmn[1] = a.y; pmx[0] = b.x; pmx[1] = b.y; psm[0] = c.x; psm[1] = c.y;
+          }
+          kmn = pmn[0]; kmx = pmx[0]; sum = __uint_as_float(psm[0]);
+#pragma unroll
+          for (int w = 1; w < NW; w++) {
+            kmn = min(kmn, pmn[w]);
+            kmx = max(kmx, pmx[w]);
+            sum += __uint_as_float(psm[w]);
+          }
         }
       } else {
         __syncwarp();
@@ -1131,7 +1237,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         // of the previous frame is cleared on the side
         static_assert(HBPL == 8 || HBPL == 4 || HBPL == 2 || HBPL == 1, "scan written for 1, 2, 4 or 8 buckets per lane");
         uint32_t ba, cnt_a, below_a, om;
-        if constexpr (HBPL <= 4) {
+        if constexpr ((SA_EXP & 0x20000) != 0) {   // timing experiment: no scan
+          for (int i = j; i < C::HSTRIDE; i += T) hist_other[i] = 0;
+          om = 1u; cnt_a = 1u; ba = 0u; below_a = ra;
+        } else if constexpr (HBPL <= 4) {
           // one level: HBPL buckets per lane (one vector load), a warp scan of the lane sums, then the
           // owner lane's buckets are broadcast and searched
           uint32_t hb[HBPL];
@@ -1144,10 +1253,23 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
           for (int b = 0; b < HBPL; b++) local += hb[b];
           uint32_t incl = local;
+#ifndef SA_BSCAN
+#define SA_BSCAN 0
+#endif
+          // inclusive prefix sums of the lane totals.  Small totals (the usual case: < 64 keys per lane) by six
+          // INDEPENDENT vote + popcount pairs, one per bit -- the latency of one vote instead of a chain of five
+          // dependent shuffles; larger totals by the shuffle scan.
+          if (SA_BSCAN && !__any_sync(0xffffffffu, local >= 64u)) {
+            const uint32_t le = 0xffffffffu >> (31 - lane);
+            incl = 0u;
 #pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += o;
+            for (int b = 0; b < 6; b++) incl += (uint32_t)__popc(__ballot_sync(0xffffffffu, (local >> b) & 1u) & le) << b;
+          } else {
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+              if (lane >= off) incl += o;
+            }
           }
           om = __ballot_sync(0xffffffffu, nbelow + incl > ra);
           if (ra < nbelow) om = 0u;
@@ -1193,8 +1315,56 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         cnt_a = __shfl_sync(0xffffffffu, h8, b8);
         below_a = c0o + __shfl_sync(0xffffffffu, incl8 - h8, b8);
         }
+        if (SA_EXP & 0x4000) { om = 1u; cnt_a = 1u; ba = 0u; below_a = ra; }   // timing experiment: the fast path always "succeeds"
         const uint32_t lo_a = winL + (ba << shw), bw = (1u << shw) - 1u;
         if (om != 0u && cnt_a <= 32u) {
+          if constexpr (DEFRANK) {
+            // Every thread keeps its (almost always at most one) candidate of the selected bucket in its own word of
+            // a table -- an unconditional store: no branch, no atomic, no return value to wait for.  Further candidates
+            // of the same thread (rare) go to an overflow list.  The median is picked from the table one group barrier
+            // later (deferred_select, after the first exchange barrier of the group's next frame).
+            if (shw == 0) {
+              // buckets are single keys: the median is lo_a itself; the record thread writes it with the record
+              if (rec_thread) { pend_med = true; pend_medkey = lo_a; misc[MI_GUESS] = lo_a; }
+            } else {
+              // c_i = min(key_i - lo_a, bw + 1) in one instruction each (the difference wraps for keys below the bucket):
+              // <= bw exactly for the keys of the bucket.  Their minimum is this thread's candidate; the sum of the
+              // c_i tells whether it is the only one (sum == 15 (bw + 1) + minimum), without a test per value.
+              constexpr uint32_t NONE = 0xffffffffu;
+              const uint32_t nlo = 0u - lo_a, cap = bw + 1u;
+              uint32_t c[E];
+#pragma unroll
+              for (int i = 0; i < E; i++) c[i] = __viaddmin_u32(v2_key<MODE>(val[i]), nlo, cap);
+              uint32_t m = cap, sm = 0u;
+              if (!(SA_EXP & 0x400)) {
+#pragma unroll
+                for (int i = 0; i < E; i += 2) { m = __vimin3_u32(m, c[i], c[i + 1]); sm += c[i] + c[i + 1]; }
+              }
+              const bool hit = m <= bw;
+              if (!(SA_EXP & 0x100000)) cand[j] = hit ? m + lo_a : NONE;          // NONE is never the key of a finite value
+              if (!(SA_EXP & 0x100000) && hit && sm != (uint32_t)(E - 1) * cap + m) {
+                // rare: several candidates in this thread -- all but one instance of the minimum go to the overflow list
+                bool skipped = false;
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                  if (c[i] <= bw) {
+                    if (c[i] == m && !skipped) skipped = true;
+                    else list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = c[i] + lo_a;
+                  }
+                }
+              }
+              if (valid_mid) {   // thread 0: the bin it owns on top of its sixteen
+                const uint32_t k = v2_key<MODE>(vmid);
+                if ((k - lo_a) <= bw) list[atomicAdd(&misc[MI_LCOUNT], 1u) & 31u] = k;
+              }
+              if (rec_thread) {
+                pend_med = false;
+                *reinterpret_cast<uint4 *>(&misc[MI_DEF]) = make_uint4((SA_EXP & 0x200000) ? 0u : cnt_a, ra - below_a, (uint32_t)cur, (uint32_t)(cur >> 32));
+              }
+            }
+            if (rec_thread) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_avg = __fdiv_rn(sum, (float)count); }
+            gw = max(gw - (gw >> SA_GW_SHRINK), GW_MIN);
+          } else {
           if (shw == 0) {
             // buckets are single keys: the median is lo_a itself; thread 0 writes it with the record
             if (rec_thread) { pend_med = true; pend_medkey = lo_a; misc[MI_GUESS] = lo_a; }
@@ -1277,6 +1447,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
           }
           if (rec_thread) { pend = true; pend_cur = cur; pend_kmn = kmn; pend_kmx = kmx; pend_avg = __fdiv_rn(sum, (float)count); }
           gw = max(gw - (gw >> SA_GW_SHRINK), GW_MIN);
+          }
         } else {
           // the guessed window missed the middle rank, or its bucket is crowded: exact loop below
           group_sync<T>(g);                                   // every warp has finished scanning
@@ -1482,6 +1653,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   }
   if (want_stats && !C::SPLIT) {
     group_sync<T>(g);                 // every thread of the group has finished its last frame
+    if (want_median) deferred_select();
     if (rec_thread) flush_record();
   }
 }

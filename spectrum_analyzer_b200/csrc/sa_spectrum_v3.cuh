@@ -25,29 +25,6 @@
 
 namespace sa {
 
-// 4 keys of one 16-byte chunk: is any of them inside the candidate range [c_lo, c_lo + c_w]?  9 instructions.
-__device__ __forceinline__ uint32_t chunk_hit(const uint4 k, uint32_t c_lo, uint32_t c_w) {
-  uint32_t hit;
-  asm("{\n.reg .pred p, q;\n.reg .u32 d0, d1, d2, d3;\n"
-      "sub.u32 d0, %1, %5;\n sub.u32 d1, %2, %5;\n sub.u32 d2, %3, %5;\n sub.u32 d3, %4, %5;\n"
-      "setp.le.u32 p, d0, %6;\n setp.le.u32 q, d1, %6;\n setp.le.or.u32 p, d2, %6, p;\n setp.le.or.u32 q, d3, %6, q;\n"
-      "or.pred p, p, q;\n selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(hit) : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(c_lo), "r"(c_w));
-  return hit;
-}
-// shared-memory atomic as a single instruction (the compiler's warp-aggregated expansion of atomicAdd(.., 1) costs
-// more than the whole test it would sit in; at most a few lanes are active where this is used)
-__device__ __forceinline__ uint32_t atoms_add(uint32_t *addr, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;\n" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ uint32_t atoms_inc(uint32_t *addr) {
-  uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], 1;\n" : "=r"(old) : "r"(smem_u32(addr)) : "memory");
-  return old;
-}
-
 // ---- bulk asynchronous copy shared -> global (TMA, 1-D), bulk-group completion ------------------------------
 __device__ __forceinline__ void bulk_copy_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"

@@ -31,10 +31,12 @@ def test_spectrum_and_visualize_sine_waves_50_1000_3777hz(sa):              # mo
         assert hann.freq_val_closest(fr)[1] > 0.85
     assert hann.freq_val_exact(500.0) < 0.00001
     assert hann.freq_val_closest(500.0)[1] < 0.00001
-    # fused window == caller-side window
+    # fused window vs caller-side window: the tuned kernels multiply by the window with a packed multiply that ptxas
+    # contracts into the first butterfly additions (FFMA2), so half of the windowed samples are never rounded on their
+    # own; the two spectra agree to a few ulp of the frame maximum (1.0 here), not bit for bit
     fused = sa.samples_fft_to_spectrum(window, 44100, sa.FrequencyLimit.Max(4000.0), sa.scaling.scale_to_zero_to_one,
                                        window="hann")
-    assert np.array_equal(fused.values(), hann.values())
+    assert np.abs(fused.values() - hann.values()).max() <= 4 * np.finfo(np.float32).eps
     # against the oracle, per bin
     for name, kind in [("no-window", O.WINDOW_NONE), ("hamming", O.WINDOW_HAMMING), ("hann", O.WINDOW_HANN),
                        ("bh4", O.WINDOW_BH4), ("bh7", O.WINDOW_BH7)]:
