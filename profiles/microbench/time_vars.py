@@ -9,11 +9,18 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=393216)
 ap.add_argument("--stats", type=int, default=7)
 ap.add_argument("--steps", type=int, default=6)
+ap.add_argument("--n", type=int, default=4096)
+ap.add_argument("--hop", type=int, default=0, help="samples between frames (default: n)")
+ap.add_argument("--scaling", type=int, default=2, help="sa_scaling_kind (2 = divide_by_N_sqrt)")
+ap.add_argument("--window", type=int, default=1, help="sa_window_kind (1 = Hann)")
+ap.add_argument("--limit", nargs=3, default=["0", "0", "0"], help="limit kind, lo, hi")
 ap.add_argument("names", nargs="+")
 a = ap.parse_args()
 root = os.getcwd()
-n, frames = 4096, a.frames
-x = torch.empty(frames * n, dtype=torch.float32, device="cuda")
+n, frames = a.n, a.frames
+hop = a.hop or n
+lk, llo, lhi = int(a.limit[0]), float(a.limit[1]), float(a.limit[2])
+x = torch.empty((frames - 1) * hop + n, dtype=torch.float32, device="cuda")
 out = torch.empty(frames * (n // 2 + 1), dtype=torch.float32, device="cuda")
 st = torch.empty(frames * 8, dtype=torch.int32, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
@@ -41,7 +48,7 @@ for name in a.names:
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     blo, nb = C.c_uint32(), C.c_uint32()
     def run():
-        r = lib.sa_spectrum_batched(ctx, x.data_ptr(), frames, n, n, 44100, 0, 0.0, 0.0, 1, 2, a.stats,
+        r = lib.sa_spectrum_batched(ctx, x.data_ptr(), frames, n, hop, 44100, lk, llo, lhi, a.window, a.scaling, a.stats,
                                     out.data_ptr(), n // 2 + 1, st.data_ptr() if a.stats else None, C.byref(blo), C.byref(nb))
         assert r == 0, r
     for _ in range(3): run()
@@ -53,4 +60,6 @@ for name in a.names:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     fps = frames / ms * 1e3
-    print(f"{name:16s} {fps / 1e6:8.2f} M spectra/s  frac {fps * 24612 / 1e9 / peak:.3f}  (stats={a.stats})", flush=True)
+    bpf = 4 * hop + 4 * nb.value + 32          # algorithmic bytes per frame
+    print(f"{name:16s} {fps / 1e6:8.2f} M spectra/s  frac {fps * bpf / 1e9 / peak:.3f}  (n={n} hop={hop} scaling={a.scaling} "
+          f"window={a.window} limit={lk} stats={a.stats} bins={nb.value})", flush=True)

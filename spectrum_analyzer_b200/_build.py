@@ -34,6 +34,11 @@ def _nvcc() -> str:
 
 
 def is_stale() -> bool:
+    if os.environ.get("SA_LIB_PATH"):
+        # an explicitly chosen build (experiment variant) is never rebuilt over: it either exists or the load fails
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"SA_LIB_PATH={LIB_PATH} does not exist")
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

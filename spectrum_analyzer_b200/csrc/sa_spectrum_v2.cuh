@@ -152,6 +152,7 @@ struct V2Cfg {
 enum { MI_KMIN = 0, MI_KMAX = 16, MI_SUM = 32, MI_ARGMIN = 48, MI_ARGMAX = 49, MI_LCOUNT = 50,
        MI_GUESS = 51, MI_SELA = 52 /*b, below, cnt*/, MI_LDONE = 55, MI_SELB = 56, MI_RESA = 57, MI_RESB = 58,
        MI_FLAGS = 59, MI_WINL = 60 /* SPLIT: two windows published by the statistics warp: {klo, shift | use << 8} per frame parity */,
+       MI_BFREE = 91 /* EARLY: warps that have read their last-pass inputs */,
        MI_DEF = 92 /* deferred ranking: {candidates, wanted rank, frame lo, frame hi} (16-byte aligned) */,
        MI_UMAX = 64, MI_BMIN = 80, MI_BMAX = 88 /* SPLIT: per warp, the lanes that hold the warp's minimum / maximum */ };
 // misc words of a group in the split variant (the words above except MI_UMAX are unused there).  [s]: hand-over slot
@@ -173,6 +174,13 @@ __device__ __forceinline__ uint32_t hist_slot(uint32_t k, uint32_t klo, int sh) 
     const int d1 = ((int)(k - klo) >> sh) + 1;      // arithmetic shift: negative when k < klo
     return (uint32_t)__vimin_s32_relu(d1, NB + 1);   // one instruction: max(min(d1, NB + 1), 0)
   }
+}
+
+// One step of an inclusive warp scan: v += (value of lane - off), for the lanes that have such a lane.  The shuffle's own
+// "source lane in range" predicate guards the add: two instructions instead of shuffle + compare + select + add.
+__device__ __forceinline__ uint32_t scan_step_up(uint32_t v, int off) {
+  asm("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}\n" : "+r"(v) : "r"(off));
+  return v;
 }
 
 template <int T>
@@ -293,6 +301,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   uint64_t *mb_full = reinterpret_cast<uint64_t *>(sync_base);        // [slot] NW arrivals: values + partials of a frame are in place
   uint64_t *mb_empty = reinterpret_cast<uint64_t *>(sync_base + 16);  // [slot] 1 arrival: the statistics warp is done with them
   uint32_t *bfree_cnt = reinterpret_cast<uint32_t *>(sync_base + 32);  // warps that have read their last-pass inputs: the last one stages the next frame
+  uint32_t *bfree = C::SPLIT ? bfree_cnt : &misc[MI_BFREE];
   float *vbuf0 = reinterpret_cast<float *>(sync_base + C::G_SYNC);    // [slot] copies of the scaled values
   uint32_t ephase = 0;               // bit s = parity of the next wait on empty[s]
   uint32_t fcount = 0;               // frames handed over so far
@@ -307,6 +316,14 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // (profiles/README.md, round 2: 0.63 -> 0.70 of the roofline with that chain removed).
   constexpr bool DEFRANK = SA_DEFRANK && !C::SPLIT;
   constexpr int RANKW = NW > 1 ? 1 : 0;      // logical warp of the group that ranks
+#ifndef SA_EARLYSTAGE
+#define SA_EARLYSTAGE 1
+#endif
+  // EARLY (launches without statistics only): the bulk copy of the group's next frame into the second exchange buffer is
+  // issued by the LAST warp that has used its last-pass inputs from it (a counter in shared memory) instead of after an
+  // extra group barrier: 0.83 -> 0.89 of the roofline at cfg2 without statistics.  With statistics the copy hangs on
+  // the statistics barrier; issuing it earlier measured SLOWER there (0.660 -> 0.649).
+  constexpr bool EARLY = SA_EARLYSTAGE && C::ALIAS && !C::SPLIT;
 #ifndef SA_GW_MIN_LOG2
 #define SA_GW_MIN_LOG2 17
 #endif
@@ -411,7 +428,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // window multiplier from global memory (rare paths only)
   auto win1 = [&](int n) -> float { return has_win ? __ldg(p.window + n) : 1.0f; };
   for (int i = j; i < (int)(C::G_HIST / sizeof(uint32_t)); i += T) hist0[i] = 0;
-  if (j == 0) { misc[MI_DEF] = 0u; misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
+  if (j == 0) { misc[MI_BFREE] = 0u; misc[MI_DEF] = 0u; misc[MI_LCOUNT] = 0u; misc[MI_LDONE] = 0u; misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u; }
   if (j == 0) {
     mbar_init(mbar, 1);
     if constexpr (C::SPLIT) {
@@ -572,6 +589,21 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     }
   };
 
+  // EARLY: called by every warp once the values it loaded from the second exchange buffer have been USED (so the loads
+  // have completed); the last warp of the group to get here issues the bulk copy of the next frame into that buffer.
+  auto early_stage = [&](bool more_, u64 next) {
+    if constexpr (EARLY) {
+      if (want_stats) return;
+      __syncwarp();
+      if (lane == 0) {
+        if (atomicAdd(bfree, 1u) == (uint32_t)(NW - 1)) {
+          *bfree = 0u;           // next used after two group barriers
+          if (more_) stage_frame(next);
+        }
+      }
+    }
+  };
+
 #pragma unroll 1
   for (;;) {
     const bool more = frame + fstep < p.n_frames;   // group-uniform
@@ -669,8 +701,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         // here issues the bulk copy (as early as possible: the data is needed at the top of the next iteration)
         __syncwarp();
         if (lane == 0) {
-          if (atoms_add_acq_rel(bfree_cnt, 1u) == (uint32_t)(NW - 1)) {
-            *bfree_cnt = 0u;           // next used after two group barriers
+          if (atoms_add_acq_rel(bfree, 1u) == (uint32_t)(NW - 1)) {
+            *bfree = 0u;           // next used after two group barriers
             if (more) stage_frame(frame + fstep);
           }
         }
@@ -691,6 +723,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         tmem_ld16(ta + C::TM_TWR, tr);    // W_N^k of the pairs (j + 256 q), (jbB + 256 q)
         dft8(va);     // va[q] = Z[j   + 256 q]
         dft8(vb);     // vb[q] = Z[jbB + 256 q]
+        early_stage(more, frame + fstep);
         // ---- recombination (src/fft.rs:126-132 bin convention) + magnitude (src/lib.rs:366-372) ----
         // pair (k, M-k): 2X[k] = P + T, 2conj(X[M-k]) = P - T with P = A + conj(B), Q = A - conj(B), T = -i w_k Q
         auto pair_mag = [&](float2 a, float2 bq, float2 w, float &m0, float &m1) {
@@ -740,8 +773,8 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         // here issues the bulk copy (as early as possible: the data is needed at the top of the next iteration)
         __syncwarp();
         if (lane == 0) {
-          if (atoms_add_acq_rel(bfree_cnt, 1u) == (uint32_t)(NW - 1)) {
-            *bfree_cnt = 0u;           // next used after two group barriers
+          if (atoms_add_acq_rel(bfree, 1u) == (uint32_t)(NW - 1)) {
+            *bfree = 0u;           // next used after two group barriers
             if (more) stage_frame(frame + fstep);
           }
         }
@@ -884,6 +917,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
     };
 
+    if constexpr (!MIRROR) early_stage(more, frame + fstep);   // (N = 4096: right after its last-pass butterflies)
     const u64 cur = frame;
     frame += fstep;
 
@@ -1066,7 +1100,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       __syncwarp();
       if (lane == 0) mbar_arrive(mb_full + slot);
     } else {
-    if constexpr (ALIAS) {
+    if constexpr (ALIAS && !EARLY) {
       if (!want_stats) {   // no statistics barrier to hang the copy on: one extra group barrier
         group_sync<T>(g);
         if (j == 0 && more) stage_frame(frame);
@@ -1149,8 +1183,17 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         group_sync<T>(g);
         // every thread has read its last-pass inputs from the second exchange buffer: the next frame may land there
         if constexpr (ALIAS) { if (j == 0 && more) stage_frame(frame); }
-        // the NW partial results of each kind as 16-byte loads (shared-memory instructions are the expensive ones)
-        {
+        // the NW partial results of each kind as 16-byte loads (up to four warps per group; with more, holding all of
+        // them at once cost more in registers than the loads saved: N = 16384 zero-to-one -3 %)
+        if constexpr (NW > 4) {
+          kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
+#pragma unroll
+          for (int w = 1; w < NW; w++) {
+            kmn = min(kmn, misc[MI_KMIN + w]);
+            kmx = max(kmx, misc[MI_KMAX + w]);
+            sum += __uint_as_float(misc[MI_SUM + w]);
+          }
+        } else {
           uint32_t pmn[NW], pmx[NW], psm[NW];
           if constexpr (NW % 4 == 0) {
 #pragma unroll
@@ -1253,38 +1296,29 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 #pragma unroll
           for (int b = 0; b < HBPL; b++) local += hb[b];
           uint32_t incl = local;
-#ifndef SA_BSCAN
-#define SA_BSCAN 0
-#endif
-          // inclusive prefix sums of the lane totals.  Small totals (the usual case: < 64 keys per lane) by six
-          // INDEPENDENT vote + popcount pairs, one per bit -- the latency of one vote instead of a chain of five
-          // dependent shuffles; larger totals by the shuffle scan.
-          if (SA_BSCAN && !__any_sync(0xffffffffu, local >= 64u)) {
-            const uint32_t le = 0xffffffffu >> (31 - lane);
-            incl = 0u;
+          // inclusive prefix sums of the lane totals (six independent vote + popcount pairs instead of the five
+          // dependent shuffles measured SLOWER: 0.638 -> 0.623; the instructions count, not the chain)
 #pragma unroll
-            for (int b = 0; b < 6; b++) incl += (uint32_t)__popc(__ballot_sync(0xffffffffu, (local >> b) & 1u) & le) << b;
-          } else {
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-              const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-              if (lane >= off) incl += o;
-            }
-          }
+          for (int off = 1; off < 32; off <<= 1) incl = scan_step_up(incl, off);
           om = __ballot_sync(0xffffffffu, nbelow + incl > ra);
           if (ra < nbelow) om = 0u;
           const int owner = (__ffs(om) - 1) & 31;
-          uint32_t c = nbelow + __shfl_sync(0xffffffffu, incl - local, owner);
-          ba = (uint32_t)(owner * HBPL); cnt_a = 0; below_a = c;
+          // every lane searches its own buckets as if it were the owner; the owner's answer travels in ONE shuffle:
+          // bucket (8 bits) | min(count, 63) << 8 | keys below the bucket << 14  (below <= M + 1 <= 8193 < 2^14)
+          uint32_t c = nbelow + incl - local;
+          uint32_t ba_l = (uint32_t)(lane * HBPL), cnt_l = 0u, below_l = c;
           bool found = false;
 #pragma unroll
           for (int b = 0; b < HBPL; b++) {
-            const uint32_t h = __shfl_sync(0xffffffffu, hb[b], owner);
+            const uint32_t h = hb[b];
             const bool here = !found && (c + h > ra);
-            if (here) { ba = (uint32_t)(owner * HBPL + b); cnt_a = h; below_a = c; }
+            if (here) { ba_l = (uint32_t)(lane * HBPL + b); cnt_l = h; below_l = c; }
             found = found || here;
             c += h;
           }
+          static_assert(M + 1 < (1 << 14) && C::NBUCKET <= 256, "packed scan result");
+          const uint32_t pk = __shfl_sync(0xffffffffu, ba_l | (min(cnt_l, 63u) << 8) | (below_l << 14), owner);
+          ba = pk & 0xffu; cnt_a = (pk >> 8) & 63u; below_a = pk >> 14;
         } else {
         const uint4 h0 = *reinterpret_cast<const uint4 *>(hist + 1 + lane * 8);
         const uint4 h1 = *reinterpret_cast<const uint4 *>(hist + 5 + lane * 8);
