@@ -608,7 +608,11 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   for (;;) {
     const bool more = frame + fstep < p.n_frames;   // group-uniform
     {
+#if defined(SA_FRAME_WAIT_HINT)
+      mbar_wait_sleep(mbar, phase);
+#else
       mbar_wait(mbar, phase);
+#endif
       phase ^= 1u;
       if (al16) {
         if (p.in_i16) {
