@@ -16,6 +16,22 @@
 
 namespace sa {
 
+// Minimum / maximum over the T lanes of a frame (T = 2..16 lanes, 32/T frames per warp).  A redux.sync with one member
+// mask PER FRAME diverges -- the frames of a warp take turns (ncu, cfg5: 13 % of the stall samples sat on these three
+// reductions) -- whereas xor-shuffles below T stay inside every aligned group of T lanes at once with the full mask.
+template <int T>
+__device__ __forceinline__ uint32_t group_min_u32(uint32_t v) {
+#pragma unroll
+  for (int off = T / 2; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+template <int T>
+__device__ __forceinline__ uint32_t group_max_u32(uint32_t v) {
+#pragma unroll
+  for (int off = T / 2; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
 template <int LOG2N_>
 struct SmallCfg {
   static constexpr int LOG2N = LOG2N_, N = 1 << LOG2N_, M = N / 2, E = 16, T = M / 16;
@@ -224,7 +240,7 @@ __device__ __forceinline__ void spectrum_body_small(const V2Params &P, unsigned 
       }
       vmid *= 0.5f;
       if (valid_mid) ub = max(ub, __float_as_uint(vmid) & 0x7fffffffu);
-      umax = __uint_as_float(__reduce_max_sync(gmask, ub));
+      umax = __uint_as_float(group_max_u32<T>(ub));
     }
     auto scale1 = [&](float v) -> float {
       if constexpr (MODE == SCALE_MUL) return v * cscale;
@@ -278,8 +294,8 @@ __device__ __forceinline__ void spectrum_body_small(const V2Params &P, unsigned 
         sum += vmid;
       }
       const uint32_t my_kmn = kmn, my_kmx = kmx;
-      kmn = __reduce_min_sync(gmask, kmn);
-      kmx = __reduce_max_sync(gmask, kmx);
+      kmn = group_min_u32<T>(kmn);
+      kmx = group_max_u32<T>(kmx);
 #pragma unroll
       for (int off = T / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off, T);
       if (my_kmn == kmn) {
@@ -404,8 +420,8 @@ __device__ __forceinline__ void spectrum_body_small(const V2Params &P, unsigned 
               if ((k - lo_a) <= bw) ma = max(ma, k);
               if ((k - lo_b) <= bw) mb = min(mb, k);
             }
-            ma = __reduce_max_sync(gmask, ma);
-            mb = __reduce_min_sync(gmask, mb);
+            ma = group_max_u32<T>(ma);
+            mb = group_min_u32<T>(mb);
             if (split) { ka = ma; kb = mb; }
           }
           if (uselist) {
