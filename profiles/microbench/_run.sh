@@ -1,5 +1,5 @@
-T="timeout 300 python profiles/microbench/time_vars.py"
-{ $T --n 256 --frames 4194304 --scaling 2 --limit 3 50 12000 prev inregall main prev inregall main
-$T --n 512 --frames 2097152 --scaling 2 --limit 2 0 8000 prev inregall main
-$T --n 512 --frames 2097152 --scaling 0 prev inregall main
-$T --n 256 --frames 4194304 --scaling 4 --window 0 prev main; } > gpurun_out/h6.log 2>&1
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/i1_smoke.log 2>&1
+timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/i1_tests.log 2>&1
+timeout 600 python bench.py > gpurun_out/i1_bench.json 2> gpurun_out/i1_bench.err
+sleep 15
+timeout 900 python profiles/bench_configs.py > gpurun_out/i1_configs.jsonl 2> gpurun_out/i1_configs.err
