@@ -1,5 +1,2 @@
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/i1_smoke.log 2>&1
-timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/i1_tests.log 2>&1
-timeout 600 python bench.py > gpurun_out/i1_bench.json 2> gpurun_out/i1_bench.err
-sleep 15
-timeout 900 python profiles/bench_configs.py > gpurun_out/i1_configs.jsonl 2> gpurun_out/i1_configs.err
+timeout 300 python profiles/microbench/time_vars.py base2 reord base2 reord > gpurun_out/j1.log 2>&1
+SA_LIB_PATH=$PWD/profiles/microbench/variants/libsa_reord.so timeout 300 python -m pytest tests/test_median_stress_gpu.py -x -q -m gpu -k "4096" > gpurun_out/j1_tests.log 2>&1
