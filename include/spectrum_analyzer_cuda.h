@@ -175,6 +175,10 @@ int sa_bin_frequencies(uint32_t n, uint32_t sampling_rate, uint32_t bin_lo, uint
  * is read: frames of n >= 1024 samples that do not start on a 16-byte boundary are staged by bulk copies of
  * their 16-byte aligned superset, clamped at the two ends of the batch (the few bytes there are fetched by
  * ordinary loads).  16-byte aligned frames (base pointer and hop) take the fastest path.
+ * Fused window (window_kind != SA_WINDOW_NONE): for n >= 1024 the multiply by the window is contracted into the first
+ * butterfly additions (fused multiply-add), so the result is not bit-identical to windowing the samples first
+ * (sa_window_batched, or the caller's own `hann_window`, as the reference's callers do) and passing SA_WINDOW_NONE;
+ * the two differ by a few ulp of the frame maximum, far inside the 1e-4 x frame-maximum tolerance of the path.
  */
 int sa_spectrum_batched(sa_ctx *ctx, const float *d_samples, uint64_t n_frames, uint32_t n,
                         uint64_t frame_stride, uint32_t sampling_rate, int limit_kind,
