@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--stats", type=int, default=7, help="stats mask (7 = min/max + average + median)")
     ap.add_argument("--out-stride", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
