@@ -5,12 +5,17 @@ bucket narrowing, all-equal) and still give statistics that are exact functions 
 
 Every frame of every batch is checked against torch's exact order statistics on the device and a sample
 against the oracle's stable-sort statistics (src/spectrum.rs:481-539)."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle as O
 
 pytestmark = pytest.mark.gpu
+
+# soak runs: SA_STRESS_SEED=k shifts every generator seed (profiles/README.md: eight seeds after the round-2 median changes)
+SEED0 = int(os.environ.get("SA_STRESS_SEED", "0")) * 1000003
 
 
 def _adversarial_batch(rng, frames, n):
@@ -63,7 +68,15 @@ def _check(torch, sa, x, n, limit, scaling, window, sr=44100):
         s = O.calc_statistics(hv[f], r.bin_lo)
         assert (s.min_val, s.min_bin, s.max_val, s.max_bin, s.median) == \
             (hs["min_val"][f], hs["min_bin"][f], hs["max_val"][f], hs["max_bin"][f], hs["median"][f]), f
-        assert abs(s.average - hs["average"][f]) <= 1e-4 * max(abs(s.max_val), abs(s.min_val), 1e-30)
+        # average: the GPU sums pairwise (error ~ log2(n) ulp of mean|v|), the reference folds the sorted copy sequentially
+        # in f32 (src/spectrum.rs:505-508: error up to ~ n ulp -- for 8193 near-equal values it leaves [min, max]).  Each
+        # is checked against the f64 mean with its own bound; soak seeds found frames where 1e-4 x max between the
+        # two was too tight for the REFERENCE's rounding, not for the kernel's.
+        exact = float(np.mean(hv[f].astype(np.float64)))
+        scale = max(float(np.mean(np.abs(hv[f].astype(np.float64)))), 1e-30)
+        eps = float(np.finfo(np.float32).eps)
+        assert abs(float(hs["average"][f]) - exact) <= 32 * eps * scale, (f, float(hs["average"][f]), exact)
+        assert abs(float(s.average) - exact) <= (hv[f].size + 8) * eps * scale, (f, float(s.average), exact)
 
 
 @pytest.mark.parametrize("n,frames", [(4096, 6000), (1024, 20000), (2048, 9000), (8192, 2500), (16384, 1200),
@@ -71,7 +84,7 @@ def _check(torch, sa, x, n, limit, scaling, window, sr=44100):
 def test_adversarial_sequences_all_limit(gpu_ctx, n, frames):
     import torch
     import spectrum_analyzer_b200 as sa
-    rng = np.random.default_rng(n)
+    rng = np.random.default_rng(n + SEED0)
     x = _adversarial_batch(rng, frames, n)
     for scaling, window in [(sa.scaling.divide_by_N_sqrt, "hann"), (None, None), (sa.scaling.scale_to_zero_to_one, "hamming"),
                             (sa.scaling.scale_20_times_log10, "blackman_harris_4term")]:
@@ -83,7 +96,7 @@ def test_adversarial_sequences_all_limit(gpu_ctx, n, frames):
 def test_adversarial_sequences_even_and_odd_counts(gpu_ctx, n, limit):
     import torch
     import spectrum_analyzer_b200 as sa
-    rng = np.random.default_rng(n + 1)
+    rng = np.random.default_rng(n + 1 + SEED0)
     frames = 3000 if n >= 4096 else 12000
     x = _adversarial_batch(rng, frames, n)
     for hi_adj in (0.0, 11.0 * 44100 / n):     # shift the upper limit by some bins: covers even and odd bin counts
@@ -96,7 +109,7 @@ def test_stationary_then_jump_sequence(gpu_ctx):
     """Long stationary run (window shrinks to its floor) followed by abrupt level changes."""
     import torch
     import spectrum_analyzer_b200 as sa
-    rng = np.random.default_rng(99)
+    rng = np.random.default_rng(99 + SEED0)
     n, frames = 4096, 20000
     x = rng.standard_normal((frames, n)).astype(np.float32)
     x[12000:] *= np.float32(1.0001)        # tiny drift: still inside the window
