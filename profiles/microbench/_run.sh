@@ -1,1 +1,8 @@
-for k in 0 1 2 3 4 5 6 7 8 9 10 11 12; do SA_STRESS_SEED=$k timeout 600 python -m pytest tests/test_median_stress_gpu.py -q -m gpu 2>&1 | grep -E "^E   |FAILED|passed|failed" | head -8; done > gpurun_out/m3_soak.log 2>&1
+T="timeout 300 python profiles/microbench/time_vars.py"
+{ $T --n 16384 --frames 65536 --scaling 3 --window 3 --stats 3 --limit 3 50 15000 prev main prev main
+$T --n 16384 --frames 65536 --scaling 3 --window 3 --stats 3 prev main
+$T --n 4096 --scaling 3 --stats 3 prev main
+$T --n 4096 --scaling 3 --stats 7 prev main
+$T --n 2048 --frames 786432 --scaling 3 --stats 1 prev main
+$T --n 8192 --frames 196608 --scaling 3 --stats 3 prev main; } > gpurun_out/n1.log 2>&1
+timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/n1_tests.log 2>&1
