@@ -86,7 +86,17 @@ struct V2Cfg {
   static constexpr int NB3 = 16 / R3;                // butterflies per thread in the third pass
   static constexpr int R4 = FOUR ? M / 4096 : 2;     // radix of the fourth (last) pass when FOUR
   static constexpr int NB4 = 16 / R4;
-  static constexpr int BUF = M + M / 16;             // padded float2 elements of one exchange buffer
+#ifndef SA_PAD18
+#define SA_PAD18 1
+#endif
+  // first exchange: every thread writes 16 consecutive values and reads stride-T ones.  One pad element per 16 (17 j + k)
+  // keeps both sides conflict-free with 8-byte accesses.  N = 16384 (one 16-warp group per SM, its stalls led by the
+  // memory-instruction queue) pads with TWO per 16 (18 j + k): the rows stay 16-byte aligned and the writes are eight
+  // STS.128 instead of sixteen STS.64 (quarter-warps hit eight distinct 16-byte columns): cfg4 0.391 -> 0.400, without
+  // statistics 0.592 -> 0.636; N = 8192 +1 %.  At N = 4096 that measured 0.662 vs 0.664, so the smaller sizes keep 17.
+  static constexpr bool PAD2 = SA_PAD18 && (M >= 4096);
+  static constexpr int PADE = PAD2 ? 8 : 16;
+  static constexpr int BUF = M + M / PADE;           // padded float2 elements of one exchange buffer
   // median histogram: 64 buckets per pass (measured with the warp-cooperative ranking: 32 buckets 1.49e8,
   // 64: 1.57e8, 128: 1.56e8, 256: 1.53e8 spectra/s at cfg2; -DSA_HBITS=n rebuilds with another count)
 #ifndef SA_HBITS
@@ -261,7 +271,7 @@ __device__ __forceinline__ uint32_t v2_binof(int j, int i) {
 template <class C, int MODE, bool FULL>
 __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned char *smem, const uint32_t tm_base) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, G = C::G, NW = C::NW, R3 = C::R3, NB3 = C::NB3;
-  constexpr int PADT = T + T / 16;  // padded stride of the strided reads (first exchange only)
+  constexpr int PADT = T + T / C::PADE;  // padded stride of the strided reads (first exchange only)
   // N = 4096: thread j runs the two last-pass butterflies j and 256-j (thread 0: 0 and 128), whose
   // outputs are exactly each other's mirror bins Z[k] <-> Z[M-k]: the real-FFT recombination then
   // needs no exchange and no barrier.
@@ -660,9 +670,15 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     // ---- pass 1: radix 16, NS = 1 (no twiddles) -------------------------------------------------
     dft16(x);
     {
-      float2 *w = wbuf + 17 * j;  // pad(16 j + k) = 17 j + k
+      if constexpr (C::PAD2) {
+        float4 *w = reinterpret_cast<float4 *>(wbuf + 18 * j);  // pad(16 j + k) = 18 j + k: 16-byte aligned rows
 #pragma unroll
-      for (int k = 0; k < 16; k++) w[k] = x[k];
+        for (int k = 0; k < 16; k += 2) w[k / 2] = make_float4(x[k].x, x[k].y, x[k + 1].x, x[k + 1].y);
+      } else {
+        float2 *w = wbuf + 17 * j;  // pad(16 j + k) = 17 j + k
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[k] = x[k];
+      }
     }
     group_sync<T>(g);
     // every thread of the group has consumed the staged samples and finished the previous frame
@@ -670,7 +686,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     if constexpr (!C::SPLIT) { if (want_stats && rec_thread) flush_record(); }
     if (want_median) deferred_select();
     {
-      const float2 *r = wbuf + (j + (j >> 4));
+      const float2 *r = wbuf + (j + (C::PAD2 ? 2 : 1) * (j >> 4));
 #pragma unroll
       for (int s = 0; s < 16; s++) x[s] = r[s * PADT];
     }
@@ -954,8 +970,12 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       if constexpr (NW > 1) {
         if (lane == 0) misc[MI_UMAX + wig] = ub;
         group_sync<T>(g);
+        if constexpr (NW > 4) {
+          ub = __reduce_max_sync(0xffffffffu, lane < NW ? misc[MI_UMAX + lane] : 0u);
+        } else {
 #pragma unroll
-        for (int w = 0; w < NW; w++) ub = max(ub, misc[MI_UMAX + w]);
+          for (int w = 0; w < NW; w++) ub = max(ub, misc[MI_UMAX + w]);
+        }
       }
       umax = __uint_as_float(ub);
     }
@@ -1190,13 +1210,17 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         // the NW partial results of each kind as 16-byte loads (up to four warps per group; with more, holding all of
         // them at once cost more in registers than the loads saved: N = 16384 zero-to-one -3 %)
         if constexpr (NW > 4) {
-          kmn = misc[MI_KMIN]; kmx = misc[MI_KMAX]; sum = __uint_as_float(misc[MI_SUM]);
+          // eight or sixteen partial results of each kind: lane w of every warp loads the w-th and the warp reduces them
+          // (3 loads + 2 redux + log2(NW) shuffles instead of 3 NW loads and as many min / max / add; the groups of
+          // these sizes are limited by the memory-instruction queue, profiles/r02b_cfg4_ncu_lines.txt)
+          const bool has = lane < NW;
+          const uint32_t pmn = has ? misc[MI_KMIN + lane] : 0xffffffffu, pmx = has ? misc[MI_KMAX + lane] : 0u;
+          float ps = has ? __uint_as_float(misc[MI_SUM + lane]) : 0.f;
+          kmn = __reduce_min_sync(0xffffffffu, pmn);
+          kmx = __reduce_max_sync(0xffffffffu, pmx);
 #pragma unroll
-          for (int w = 1; w < NW; w++) {
-            kmn = min(kmn, misc[MI_KMIN + w]);
-            kmx = max(kmx, misc[MI_KMAX + w]);
-            sum += __uint_as_float(misc[MI_SUM + w]);
-          }
+          for (int off = NW / 2; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+          sum = __shfl_sync(0xffffffffu, ps, 0);
         } else {
           uint32_t pmn[NW], pmx[NW], psm[NW];
           if constexpr (NW % 4 == 0) {
