@@ -537,6 +537,36 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
     misc[MI_ARGMIN] = 0xffffffffu; misc[MI_ARGMAX] = 0u; misc[MI_FLAGS] = 0u;
   };
 
+  // bin index of val[i]
+  auto binof = [&](int i) -> uint32_t {
+    if constexpr (MIRROR) {
+      const int q = i >> 2, r = i & 3;
+      const uint32_t k = (uint32_t)(((r & 2) ? jbB : j) + 256 * q);
+      return (r & 1) ? (uint32_t)M - k : k;
+    } else if constexpr (MIRG) {
+      const int pidx = i >> 1, sl = pidx / LR, rem = pidx % LR;
+      const uint32_t k = (uint32_t)(((rem & 1) ? bfB(sl) : bfA(sl)) + (rem >> 1) * LS);
+      return (i & 1) ? (uint32_t)M - k : k;
+    } else {
+      const uint32_t k = (uint32_t)(beta + (i >> 1) * 256);
+      return (i & 1) ? (uint32_t)M - k : k;
+    }
+  };
+
+  // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 16 (+1) owned bins -- the same for every frame, so
+  // it is computed once (limited ranges +1 %).  Skipping values that NO lane of a warp keeps by warp-uniform branches
+  // was measured too: the branches cost more than the predicated work they skip (cfg4 0.415 -> 0.358, Max(4000) -7 %).
+  uint32_t valid = 0xffffffffu;
+  const bool valid_mid = (j == 0) && (FULL || ((uint32_t)(M / 2) >= lo && (uint32_t)(M / 2) <= hi));
+  if constexpr (!FULL) {
+    valid = 0;
+#pragma unroll
+    for (int i = 0; i < E; i++) {
+      const uint32_t b = binof(i);
+      valid |= (b >= lo && b <= hi) ? (1u << i) : 0u;
+    }
+  }
+
   // DEFRANK: median of the group's previous frame from the candidate table (complete: a group barrier has passed since
   // the last store to it) -- the `want`-th smallest of the `cnt` keys in it (src/spectrum.rs:515-524 sorts; equal keys
   // are equal values, so ties need no order).  One warp; each lane holds T/32 table words plus one overflow key.
@@ -921,38 +951,11 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         }
       }
     }
-    // bin index of val[i]
-    auto binof = [&](int i) -> uint32_t {
-      if constexpr (MIRROR) {
-        const int q = i >> 2, r = i & 3;
-        const uint32_t k = (uint32_t)(((r & 2) ? jbB : j) + 256 * q);
-        return (r & 1) ? (uint32_t)M - k : k;
-      } else if constexpr (MIRG) {
-        const int pidx = i >> 1, sl = pidx / LR, rem = pidx % LR;
-        const uint32_t k = (uint32_t)(((rem & 1) ? bfB(sl) : bfA(sl)) + (rem >> 1) * LS);
-        return (i & 1) ? (uint32_t)M - k : k;
-      } else {
-        const uint32_t k = (uint32_t)(beta + (i >> 1) * 256);
-        return (i & 1) ? (uint32_t)M - k : k;
-      }
-    };
-
     if constexpr (!MIRROR) early_stage(more, frame + fstep);   // (N = 4096: right after its last-pass butterflies)
     const u64 cur = frame;
     frame += fstep;
 
-    // ---- FrequencyLimit slice (src/lib.rs:286-304): validity of the 32 (+1) owned bins -----------
-    uint32_t valid = 0xffffffffu;
-    bool valid_mid = (j == 0);
-    if constexpr (!FULL) {
-      valid = 0;
-#pragma unroll
-      for (int i = 0; i < E; i++) {
-        const uint32_t b = binof(i);
-        valid |= (b >= lo && b <= hi) ? (1u << i) : 0u;
-      }
-      valid_mid = valid_mid && ((uint32_t)(M / 2) >= lo && (uint32_t)(M / 2) <= hi);
-    }
+    // FrequencyLimit slice: `valid` and `valid_mid` are launch constants, computed once in front of the frame loop
 #define SA_VALID(i) (FULL || ((valid >> (i)) & 1u))
 
     // ---- unscaled values u = 0.5*sqrt(..) and, for the modes that need it, max|u| ----------------
