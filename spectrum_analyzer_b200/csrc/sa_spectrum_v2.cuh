@@ -34,13 +34,25 @@
 //  * NaN/Inf validation (src/lib.rs:168-173) costs nothing on clean frames: any non-finite input
 //    makes every output bin non-finite, so the maximum flags it and only then the group re-reads
 //    its samples to classify NaN vs Inf vs overflow.
-//  * median (src/spectrum.rs:515-524): exact selection.  The keys are histogrammed (64 buckets +
+//  * median (src/spectrum.rs:515-524): exact selection.  The keys are histogrammed (128 buckets +
 //    below/above, unconditional shared-memory atomics) against a window guessed from the previous
 //    frame's median, fused with the min/max/sum pass; after the one statistics barrier every warp
-//    scans the histogram (two buckets per lane, one warp scan), the (typically < 10) keys of the selected bucket
-//    are appended to a list, and the warp whose thread completes the list ranks it -- nobody waits.
-//    The ranks are verified against the counts; a missed window, an even count, a crowded bucket or a
+//    scans the histogram (four buckets per lane, one warp scan, the owner lane's answer in one packed
+//    shuffle).  Candidates of the selected bucket: c_i = min(key_i - lo, width) (one VIADDMNMX per value),
+//    a 3-input-minimum tree gives the thread's candidate and the sum of the c_i tells whether it is the
+//    only one; it goes into the thread's own word of a table by an unconditional store (more of the same
+//    thread: overflow list).  ONE warp picks the median from the table right after the first exchange
+//    barrier of the group's NEXT frame (up to three keys: minimum / maximum / sum by three warp
+//    reductions; more: stripping minima).  A missed window, an even count, a crowded bucket or a
 //    non-finite frame take the barrier-synchronised exact loop (full-range histogram, narrowing passes).
+//    (Round 1 appended candidates to a list and let the warp of the last pusher rank it: that warp was
+//    the group's latest by construction and its chain held the group at its next barrier.)
+//  * the window multiply is packed (FMUL2, contracted by ptxas into the first butterfly adds) and a
+//    power-of-two scaling factor rides on the window multipliers (SA_OPT); without statistics the next
+//    frame's bulk copy is issued by the last warp that has used its last-pass inputs (EARLY);
+//    N = 8192 / 16384 write the first exchange with STS.128 into rows padded to 18 and reduce the
+//    per-warp partial results inside a warp (their groups are limited by the memory-instruction queue).
+//    DESIGN.md section 4.6 lists what each of these bought and what was measured and rejected.
 #pragma once
 #include "sa_common.cuh"
 #include "sa_dft.cuh"
@@ -680,9 +692,10 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       }
     }
 
-    // ---- window (src/windows.rs: w_i * x_i, one f32 multiply) -----------------------------------
-    // scalar mul.rn on purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would
-    // skip the rounding of the windowed sample that the reference performs (src/windows.rs:47)
+    // ---- window (src/windows.rs: w_i * x_i) -------------------------------------------------------
+    // packed by default (SA_OPT bit 0): ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, so half of the
+    // windowed samples are not rounded on their own (src/windows.rs:47 rounds each) -- see the SA_OPT note above;
+    // -DSA_OPT=2 builds the scalar mul.rn that rounds like the reference
     {
       float w[32];
       tmem_ld32(ta + C::TM_WIN, w);
