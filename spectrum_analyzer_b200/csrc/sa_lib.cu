@@ -90,7 +90,7 @@ struct sa_ctx {
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
   KernelPlan plans[16];                                     // per log2n (generic family)
-  KernelPlan plans_v2[16][4][2];                            // tuned family: [log2n][scale mode][full range]
+  KernelPlan plans_v2[16][4][2][2];                         // tuned family: [log2n][scale mode][full range][f32 input on 16-byte boundaries]
   KernelPlan plans_v3[16][4][2];                            // warp-specialised variant of the tuned family
   std::map<uint32_t, float2 *> v2_tables;                   // n -> tw2 | tw3 | twr (one allocation)
   KernelPlan plans_small[16][4][2];                         // small-N family
@@ -202,10 +202,15 @@ int get_v2_tables(sa_ctx *ctx, V2Params &P) {
   return SA_OK;
 }
 
-template <class C, int MODE, bool FULL>
+template <class C, int MODE, bool FULL, bool FASTIN = false>
 int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
-  KernelPlan &plan = ctx->plans_v2[C::LOG2N][MODE][FULL ? 1 : 0];
-  auto kernel = spectrum_kernel_v2<C, MODE, FULL>;
+  if constexpr (FULL && !FASTIN) {
+    // FrequencyLimit::All on f32 frames that all start on 16-byte boundaries: the specialisation without the per-frame
+    // input-format tests (limited ranges keep the general kernel: half the extra instantiations for the same headline)
+    if (P.b.aligned16 && !P.b.in_i16) return launch_v2_inst<C, MODE, FULL, true>(ctx, P);
+  }
+  KernelPlan &plan = ctx->plans_v2[C::LOG2N][MODE][FULL ? 1 : 0][FASTIN ? 1 : 0];
+  auto kernel = spectrum_kernel_v2<C, MODE, FULL, FASTIN>;
   if (!plan.ready) {
     SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TOTAL));
     int per_sm = 0;
@@ -218,7 +223,7 @@ int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
   const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
   kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(P);
   ctx->launches++;
-  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_v2<V2Cfg<%d,%d,0>,%d,%d>", C::LOG2N, C::G, MODE, FULL ? 1 : 0);
+  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_v2<V2Cfg<%d,%d,0>,%d,%d,%d>", C::LOG2N, C::G, MODE, FULL ? 1 : 0, FASTIN ? 1 : 0);
   SA_CUDA(cudaGetLastError());
   return SA_OK;
 }
