@@ -204,9 +204,8 @@ int get_v2_tables(sa_ctx *ctx, V2Params &P) {
 
 template <class C, int MODE, bool FULL, bool FASTIN = false>
 int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
-  if constexpr (FULL && !FASTIN) {
-    // FrequencyLimit::All on f32 frames that all start on 16-byte boundaries: the specialisation without the per-frame
-    // input-format tests (limited ranges keep the general kernel: half the extra instantiations for the same headline)
+  if constexpr (!FASTIN) {
+    // f32 frames that all start on 16-byte boundaries: the specialisation without the per-frame input-format tests
     if (P.b.aligned16 && !P.b.in_i16) return launch_v2_inst<C, MODE, FULL, true>(ctx, P);
   }
   KernelPlan &plan = ctx->plans_v2[C::LOG2N][MODE][FULL ? 1 : 0][FASTIN ? 1 : 0];
