@@ -90,7 +90,7 @@ struct sa_ctx {
   std::map<uint32_t, float2 *> twiddles;                   // n -> W_n table
   std::map<std::pair<int, uint32_t>, float *> windows;     // (kind, n) -> multipliers
   KernelPlan plans[16];                                     // per log2n (generic family)
-  KernelPlan plans_v2[16][4][2][2];                         // tuned family: [log2n][scale mode][full range][f32 input on 16-byte boundaries]
+  KernelPlan plans_v2[16][4][2][3];                         // tuned family: [log2n][scale mode][full range][general | f32 input on 16-byte boundaries | + all statistics]
   KernelPlan plans_v3[16][4][2];                            // warp-specialised variant of the tuned family
   std::map<uint32_t, float2 *> v2_tables;                   // n -> tw2 | tw3 | twr (one allocation)
   KernelPlan plans_small[16][4][2];                         // small-N family
@@ -202,14 +202,17 @@ int get_v2_tables(sa_ctx *ctx, V2Params &P) {
   return SA_OK;
 }
 
-template <class C, int MODE, bool FULL, bool FASTIN = false>
+template <class C, int MODE, bool FULL, bool FASTIN = false, int SMASK = -1>
 int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
   if constexpr (!FASTIN) {
     // f32 frames that all start on 16-byte boundaries: the specialisation without the per-frame input-format tests
     if (P.b.aligned16 && !P.b.in_i16) return launch_v2_inst<C, MODE, FULL, true>(ctx, P);
+  } else if constexpr (SMASK < 0) {
+    // ... and with all statistics wanted (what the reference always computes): the mask is a constant as well
+    if (P.b.stats != nullptr && P.b.stats_mask == SA_STATS_ALL) return launch_v2_inst<C, MODE, FULL, true, (int)SA_STATS_ALL>(ctx, P);
   }
-  KernelPlan &plan = ctx->plans_v2[C::LOG2N][MODE][FULL ? 1 : 0][FASTIN ? 1 : 0];
-  auto kernel = spectrum_kernel_v2<C, MODE, FULL, FASTIN>;
+  KernelPlan &plan = ctx->plans_v2[C::LOG2N][MODE][FULL ? 1 : 0][FASTIN ? (SMASK >= 0 ? 2 : 1) : 0];
+  auto kernel = spectrum_kernel_v2<C, MODE, FULL, FASTIN, SMASK>;
   if (!plan.ready) {
     SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TOTAL));
     int per_sm = 0;
@@ -222,7 +225,7 @@ int launch_v2_inst(sa_ctx *ctx, const V2Params &P) {
   const unsigned grid = (unsigned)std::min<u64>(needed, (u64)plan.max_blocks);
   kernel<<<grid, C::NT, C::SMEM_TOTAL, ctx->stream>>>(P);
   ctx->launches++;
-  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_v2<V2Cfg<%d,%d,0>,%d,%d,%d>", C::LOG2N, C::G, MODE, FULL ? 1 : 0, FASTIN ? 1 : 0);
+  snprintf(ctx->last_kernel, sizeof ctx->last_kernel, "sa::spectrum_kernel_v2<V2Cfg<%d,%d,0>,%d,%d,%d,%d>", C::LOG2N, C::G, MODE, FULL ? 1 : 0, FASTIN ? 1 : 0, SMASK);
   SA_CUDA(cudaGetLastError());
   return SA_OK;
 }

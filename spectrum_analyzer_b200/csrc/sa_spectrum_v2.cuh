@@ -282,7 +282,9 @@ __device__ __forceinline__ uint32_t v2_binof(int j, int i) {
 
 // FASTIN: the launch's input is f32 with every frame on a 16-byte boundary (the common case) -- the two run-time
 // format tests in front of every frame's loads become compile-time constants (cfg2 +1.5 %).
-template <class C, int MODE, bool FULL, bool FASTIN = false>
+// SMASK >= 0: the statistics mask is a compile-time constant too (7: minimum / maximum + average + median, the mask the
+// reference's `FrequencySpectrum::new` implies) -- the per-frame tests of `stats` / `stats_mask` disappear.
+template <class C, int MODE, bool FULL, bool FASTIN = false, int SMASK = -1>
 __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned char *smem, const uint32_t tm_base) {
   constexpr int N = C::N, M = C::M, E = C::E, T = C::T, G = C::G, NW = C::NW, R3 = C::R3, NB3 = C::NB3;
   constexpr int PADT = T + T / C::PADE;  // padded stride of the strided reads (first exchange only)
@@ -466,8 +468,9 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
 
   const uint32_t lo = p.bin_lo, hi = p.bin_hi;
   const uint32_t count = hi - lo + 1;
-  const bool want_stats = p.stats != nullptr;
-  const bool want_median = want_stats && (p.stats_mask & SA_STATS_MEDIAN);
+  const uint32_t smask = SMASK >= 0 ? (uint32_t)SMASK : p.stats_mask;
+  const bool want_stats = SMASK >= 0 ? (SMASK != 0) : (p.stats != nullptr);
+  const bool want_median = want_stats && (smask & SA_STATS_MEDIAN);
   const float cscale = P.cmul;
 
   u64 frame = (u64)blockIdx.x * G + g;
@@ -533,7 +536,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   // by the "last pusher"), then reset the per-frame words.  Called right after a group barrier.
   auto flush_record = [&]() {
     if (pend && !(SA_EXP & 1)) {
-      const bool mm = p.stats_mask & SA_STATS_MINMAX;
+      const bool mm = smask & SA_STATS_MINMAX;
       uint4 r0;
       r0.x = mm ? __float_as_uint(v2_unkey<MODE>(pend_kmn)) : 0u;
       r0.y = mm ? misc[MI_ARGMIN] : 0u;
@@ -541,7 +544,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
       r0.w = mm ? misc[MI_ARGMAX] : 0u;
       uint32_t *rec = reinterpret_cast<uint32_t *>(&p.stats[pend_cur]);
       *reinterpret_cast<uint4 *>(rec) = r0;
-      rec[4] = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(pend_avg) : 0u;
+      rec[4] = (smask & SA_STATS_AVERAGE) ? __float_as_uint(pend_avg) : 0u;
       if (pend_med) rec[5] = want_median ? __float_as_uint(v2_unkey<MODE>(pend_medkey)) : 0u;
       const uint32_t fl = misc[MI_FLAGS];
       const uint32_t st = (fl & 1u) ? SA_ERR_NAN_VALUES : (fl & 2u) ? SA_ERR_INFINITY_VALUES
@@ -1687,13 +1690,13 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
         if (j == 0) {
           // a group barrier has passed since the arg-bin / flag atomics: write the record now
           misc[MI_GUESS] = kb;
-          const bool mm = p.stats_mask & SA_STATS_MINMAX;
+          const bool mm = smask & SA_STATS_MINMAX;
           uint4 r0, r1;
           r0.x = mm ? __float_as_uint(v2_unkey<MODE>(kmn)) : 0u;
           r0.y = mm ? misc[MI_ARGMIN] : 0u;
           r0.z = mm ? __float_as_uint(v2_unkey<MODE>(kmx)) : 0u;
           r0.w = mm ? misc[MI_ARGMAX] : 0u;
-          r1.x = (p.stats_mask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(sum, (float)count)) : 0u;
+          r1.x = (smask & SA_STATS_AVERAGE) ? __float_as_uint(__fdiv_rn(sum, (float)count)) : 0u;
           const float med = (count & 1u) ? v2_unkey<MODE>(kb)
                                          : __fdiv_rn(__fadd_rn(v2_unkey<MODE>(ka), v2_unkey<MODE>(kb)), 2.0f);
           r1.y = __float_as_uint(med);
@@ -1739,7 +1742,7 @@ __device__ __forceinline__ void spectrum_body_v2(const V2Params &P, unsigned cha
   }
 }
 
-template <class C, int MODE, bool FULL, bool FASTIN = false>
+template <class C, int MODE, bool FULL, bool FASTIN = false, int SMASK = -1>
 __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P) {
   extern __shared__ __align__(16) unsigned char smem[];
   // tensor-memory allocation for the per-thread tables (one warp allocates, everybody reads the address)
@@ -1749,7 +1752,7 @@ __global__ void __launch_bounds__(C::NT, 1) spectrum_kernel_v2(const V2Params P)
   __syncthreads();
   tmem_fence_after_sync();
   const uint32_t tm_base = *slot;
-  spectrum_body_v2<C, MODE, FULL, FASTIN>(P, smem, tm_base);
+  spectrum_body_v2<C, MODE, FULL, FASTIN, SMASK>(P, smem, tm_base);
   // groups finish at different times: the allocation is released once every thread is done with it
   tmem_fence_before_sync();
   __syncthreads();
